@@ -1,0 +1,187 @@
+/*
+ * yolo_b200.h -- C ABI of libyolo_b200.so: the B200-native (sm_100a) YOLO TEST hot path.
+ *
+ * The reference (wns349/tensorflow-yolo) is pure Python over TensorFlow 1.x and has no FFI of its
+ * own; its boundary for this path is the Python protocol of net/yolo.py:41-96.  Each entry point
+ * below names the reference call it replaces.  A Python shim with the reference's signatures
+ * (tensorflow_yolo_b200/net/*.py) binds these symbols through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative yb_status; yb_last_error() returns a
+ *     thread-local, human-readable message for the last failure.  Nothing aborts or throws.
+ *   - the caller owns every host buffer it passes; an engine owns all of its device memory.
+ *   - an engine is bound to one CUDA device and is not thread-safe; use one engine (and one host
+ *     thread or process) per GPU.  There is no CPU fallback: without a usable CUDA device every
+ *     compute entry point fails with YB_ERR_CUDA.
+ *   - "host" pointers are ordinary (pageable or pinned) memory; "device" pointers are CUDA device
+ *     memory on the engine's device (yb_mem says which).
+ */
+#ifndef YOLO_B200_H_
+#define YOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_ABI_VERSION 1
+#define YB_MAX_SRC 4
+#define YB_MAX_ANCHORS 16
+
+typedef enum yb_status {
+  YB_OK = 0,
+  YB_ERR_INVALID = -1,      /* bad argument / unsupported plan */
+  YB_ERR_CUDA = -2,         /* CUDA runtime or driver failure (message has the CUDA error string) */
+  YB_ERR_SHORT_WEIGHTS = -3,/* weight stream shorter than the plan needs (reference: ValueError, net/base.py:38) */
+  YB_ERR_CAPACITY = -4,     /* caller-provided output buffer too small */
+  YB_ERR_STATE = -5         /* call order violated (e.g. detect before forward) */
+} yb_status;
+
+/* plan entry kinds: one per class of the reference's net/layers.py */
+typedef enum yb_kind {
+  YB_INPUT = 0,      /* layers.py:106-109 */
+  YB_CONV = 1,       /* layers.py:17-67   conv2d_bn_act */
+  YB_MAXPOOL = 2,    /* layers.py:70-81 */
+  YB_ROUTE = 3,      /* layers.py:84-87 */
+  YB_REORG = 4,      /* layers.py:90-97 */
+  YB_SHORTCUT = 5,   /* layers.py:100-103 */
+  YB_UPSAMPLE = 6,   /* layers.py:112-116 */
+  YB_YOLO = 7,       /* layers.py:126-134 */
+  YB_DETECTION = 8   /* layers.py:119-123 */
+} yb_kind;
+
+/* One entry of the reference's flat `layers` list (net/v3.py:8-94, net/v2.py:10-60). */
+typedef struct yb_layer {
+  int kind;                 /* yb_kind */
+  int filters;              /* conv: output channels */
+  int ksize;                /* conv / maxpool window */
+  int stride;               /* conv / maxpool stride, reorg / upsample factor */
+  int batch_norm;           /* conv: 1 = batch-norm (eps 1e-5), no bias; 0 = bias */
+  int leaky;                /* conv: 1 = leaky-ReLU(0.1); 0 = linear */
+  int n_src;
+  int src[YB_MAX_SRC];      /* absolute indices into the plan */
+  int n_anchors;            /* yolo */
+  float anchors[2 * YB_MAX_ANCHORS]; /* yolo: (w,h) pairs in grid units (already divided by the stride) */
+} yb_layer;
+
+typedef enum yb_mem { YB_MEM_HOST = 0, YB_MEM_DEVICE = 1 } yb_mem;
+typedef enum yb_dtype { YB_F32 = 0, YB_U8 = 1 } yb_dtype;
+
+/* decode variants: net/v3.py:109-136 (sigmoid classes, score = objectness) and
+ * net/v2.py:93-119 (softmax classes, score = objectness * max class probability) */
+typedef enum yb_decode_mode { YB_DECODE_V3 = 0, YB_DECODE_V2 = 1 } yb_decode_mode;
+
+/* NMS variants.  YB_NMS_REFERENCE = net/base.py:195-209: class-agnostic, suppress iff IoU >= thr.
+ * YB_NMS_PER_CLASS = the optional north-star mode: per class, suppress iff IoU > thr. */
+typedef enum yb_nms_mode { YB_NMS_REFERENCE = 0, YB_NMS_PER_CLASS = 1 } yb_nms_mode;
+
+/* One detection == one reference BoundingBox (net/base.py:257-272); dtypes follow what the
+ * reference's decode produces under numpy>=2: x,y,prob float32; w,h float64. */
+typedef struct yb_det {
+  double w, h;              /* normalised size */
+  float x, y;               /* normalised centre */
+  float prob;
+  int32_t class_idx;
+  int32_t row;              /* row of net[-1].out this box was decoded from */
+  int32_t pad_;
+} yb_det;
+
+typedef struct yb_engine yb_engine;
+
+/* ---- library ---- */
+int yb_abi_version(void);
+const char* yb_last_error(void);
+/* number of visible CUDA devices (0 and YB_OK when there is no GPU / no driver) */
+int yb_device_count(int* count);
+
+/* ---- engine: replaces tf graph build + tf.Session (net/yolo.py:63,67-68) ---- */
+/* plan: the flat layer list.  decode_mode/num_classes describe the head.  For YOLOv2 (whose
+ * reference plan ends in the linear conv, net/v2.py:52-59) the caller appends one YB_YOLO entry
+ * carrying the anchors so that yb_engine_detect knows the head geometry. */
+int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int in_c,
+                     int max_batch, int device, int decode_mode, int num_classes, yb_engine** out);
+void yb_engine_destroy(yb_engine* e);
+
+/* Replaces base.load_weights + sess.run(ops) (net/base.py:26-46, net/yolo.py:74-75): consumes the
+ * darknet float32 stream (header already stripped) in plan order -- per BN conv
+ * beta,gamma,moving_mean,moving_variance,kernel[O][I][kh][kw]; per linear conv bias,kernel.
+ * *consumed receives the number of floats read (the reference prints read/len, base.py:44);
+ * a surplus is not an error, a shortfall is YB_ERR_SHORT_WEIGHTS. */
+int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* consumed);
+
+/* Replaces sess.run(net[-1].out, {net[0].out: x_batch}) (net/yolo.py:83).  images: NHWC,
+ * n*in_h*in_w*in_c elements of dtype (float32 in [0,1], or uint8 which is scaled by 1/255),
+ * in host or device memory.  Asynchronous with respect to the host on the engine's stream;
+ * results stay on the device. */
+int yb_engine_forward(yb_engine* e, const void* images, int dtype, int mem, int n);
+
+/* Copies the reference's net[-1].out for the last forward to host float32:
+ * [n, R, 5+C] (v3, net/v3.py:90-93) or [n, h, w, A*(5+C)] (v2, net/v2.py:59).  For parity tests;
+ * the detect path never materialises it.  capacity in floats. */
+int yb_engine_read_output(yb_engine* e, float* host_out, size_t capacity);
+int yb_engine_output_shape(yb_engine* e, int* rows, int* cols); /* rows = R (v3) or h*w (v2); cols = 5+C or A*(5+C) */
+
+/* Debug/parity: copies the NHWC float32 value of plan entry `layer` (as the reference's
+ * layers[layer].out) for the last forward.  shape_hwc receives h,w,c. */
+int yb_engine_read_layer(yb_engine* e, int layer, float* host_out, size_t capacity, int shape_hwc[3]);
+
+/* Replaces find_bounding_boxes (net/v3.py:139-151, net/v2.py:82-90) for the last forward:
+ * decode + threshold + NMS on the device.  out: [n][max_per_image] detections in kept
+ * (score-descending) order; counts[n].  Synchronises the engine's stream. */
+int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode,
+                     yb_det* out, int* counts, int max_per_image);
+/* Same, but leaves the results on the device (for device-timed benches); returns after enqueueing. */
+int yb_engine_detect_async(yb_engine* e, float threshold, float iou_threshold, int nms_mode);
+int yb_engine_sync(yb_engine* e);
+
+/* per-op timing of the last forward+detect, measured with CUDA events on the engine's stream:
+ * fills up to cap entries of (plan layer index or -1, milliseconds); returns the number of ops in *n_ops */
+int yb_engine_profile(yb_engine* e, const void* images, int dtype, int mem, int n,
+                      int* layer_idx, float* ms, int cap, int* n_ops);
+/* conv implementation: 0 = tcgen05/TMA implicit GEMM (default), 1 = plain CUDA-core kernel
+ * (debug cross-check only; never selected implicitly). */
+int yb_engine_set_conv_impl(yb_engine* e, int impl);
+/* number of kernel launches the last forward / detect enqueued */
+int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches);
+
+/* ---- stand-alone post-processing on caller tensors ---- */
+typedef struct yb_scale {
+  int h, w, n_anchors;
+  float anchors[2 * YB_MAX_ANCHORS];  /* grid units */
+} yb_scale;
+
+/* Opaque post-processing context for stand-alone decode+NMS over head tensors in the reference's
+ * net[-1].out layout (BASELINE config 5).  rows_per_image = sum(h*w*A). */
+typedef struct yb_post yb_post;
+int yb_post_create(const yb_scale* scales, int n_scales, int num_classes, int decode_mode,
+                   int max_batch, int device, yb_post** out);
+void yb_post_destroy(yb_post* p);
+/* head: [n, R, 5+C] float32 (v3) or [n, h, w, A*(5+C)] (v2), host or device memory.
+ * Runs decode -> sort -> NMS on the device; out/counts as in yb_engine_detect (may be NULL to
+ * leave results on the device).  cand_counts (optional, [n]) receives the number of candidates that
+ * passed the threshold before NMS. */
+int yb_post_run(yb_post* p, const float* head, int mem, int n, float threshold, float iou_threshold,
+                int nms_mode, yb_det* out, int* counts, int max_per_image, int* cand_counts);
+/* decode only: candidates of image i in undefined order (sort by row to compare), host output. */
+int yb_post_decode(yb_post* p, const float* head, int mem, int n, float threshold,
+                   yb_det* out, int* counts, int max_per_image);
+int yb_post_sync(yb_post* p);
+/* device time of the last yb_post_run split by stage, milliseconds (decode, sort+nms) */
+int yb_post_last_ms(yb_post* p, float* decode_ms, float* nms_ms);
+
+/* Replaces base.non_maximum_suppression (net/base.py:195-209) on caller boxes (host memory):
+ * x,y,w,h,prob are [k] arrays; coordinates are float64 if f64 != 0 else float32 (the IoU of
+ * net/base.py:180-192 is then evaluated in that precision, like numpy does); class_idx may be
+ * NULL for YB_NMS_REFERENCE.  iou_threshold is rounded to float32 first when f64 == 0 (numpy's
+ * weak-scalar rule).  keep receives the indices of the kept boxes in kept order, *n_keep their
+ * number. */
+int yb_nms(const void* x, const void* y, const void* w, const void* h, const float* prob,
+           const int32_t* class_idx, int k, int f64, double iou_threshold,
+           int nms_mode, int device, int32_t* keep, int* n_keep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H_ */

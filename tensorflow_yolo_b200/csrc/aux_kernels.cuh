@@ -1,0 +1,264 @@
+// aux_kernels.cuh -- the non-GEMM device kernels of the conv stack (all NHWC):
+//   conv_direct_kernel   first conv (Cin=3, fp32/u8 image in, fp32 weights) -- HBM-bound, AI ~25 flop/B
+//   conv_simt_kernel     plain CUDA-core conv on the same packed operands as the tcgen05 kernel; a
+//                        debug cross-check and the path for channel counts TMA cannot address
+//   maxpool2_kernel      net/layers.py:70-81 (2x2/2; the zero pad row/col is never read on even maps)
+//   add / upsample2 / reorg2 / copy_channels   stand-alone forms of net/layers.py:84-116, used only when
+//                        a plan does not match the fused patterns (never for YOLOv2/v3)
+//   gather_head / read_view   layout conversion for yb_engine_read_output / yb_engine_read_layer
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_tc.cuh"
+
+namespace yb {
+
+struct InView {           // activation tensor as a conv input
+  const void* ptr;        // already channel-offset
+  int ld;                 // elements per pixel
+  int H, W, C;
+};
+
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+
+// Output-pixel addressing shared by the CUDA-core kernels (same modes as the tcgen05 epilogue).
+__device__ __forceinline__ int out_pixels(const ConvArgs& a, int m, long long (&opix)[4], int& ch_extra) {
+  ch_extra = 0;
+  if (a.out_mode == OUT_PLAIN) { opix[0] = m; return 1; }
+  const int hw = a.Ho * a.Wo;
+  const int img = m / hw, rem = m - img * hw;
+  const int p = rem / a.Wo, q = rem - p * a.Wo;
+  if (a.out_mode == OUT_UPSAMPLE2) {
+    const long long W2 = 2 * a.Wo;
+    const long long base = ((long long)img * 2 * a.Ho + 2 * p) * W2 + 2 * q;
+    opix[0] = base; opix[1] = base + 1; opix[2] = base + W2; opix[3] = base + W2 + 1;
+    return 4;
+  }
+  opix[0] = ((long long)img * (a.Ho >> 1) + (p >> 1)) * (a.Wo >> 1) + (q >> 1);
+  ch_extra = ((p & 1) * 2 + (q & 1)) * a.cout;
+  return 1;
+}
+
+__device__ __forceinline__ void store_out(const ConvArgs& a, int m, int co, float y) {
+  long long opix[4];
+  int ch_extra;
+  const int nd = out_pixels(a, m, opix, ch_extra);
+  for (int d = 0; d < nd; ++d) {
+    if (a.out_f32) reinterpret_cast<float*>(a.out)[opix[d] * a.out_ld + ch_extra + co] = y;
+    else reinterpret_cast<__nv_bfloat16*>(a.out)[opix[d] * a.out_ld + ch_extra + co] = __float2bfloat16_rn(y);
+  }
+}
+
+// ---- first conv: image (fp32 or u8, C<=4) -> bf16, weights fp32 [taps*Cin][cout] ----
+// one thread = one output pixel x 32 output channels (blockIdx.y selects the channel group)
+template <bool U8>
+__global__ void __launch_bounds__(128) conv_direct_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                          const float* __restrict__ u8_lut) {
+  extern __shared__ float s_w[];   // [taps*Cin][32]
+  const int cin = in.C;
+  const int kk = a.taps * cin;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < kk * 32; i += blockDim.x) {
+    const int k = i >> 5, j = i & 31;
+    s_w[i] = (c0 + j < a.cout) ? wt[(long long)k * a.cout + c0 + j] : 0.0f;
+  }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.M) return;
+  const int hw = a.Ho * a.Wo;
+  const int img = m / hw, rem = m - img * hw;
+  const int p = rem / a.Wo, q = rem - p * a.Wo;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+  for (int kh = 0; kh < a.ksize; ++kh) {
+    const int y = p * a.conv_stride + kh - a.pad;
+    for (int kw = 0; kw < a.ksize; ++kw) {
+      const int x = q * a.conv_stride + kw - a.pad;
+      const bool inb = (y >= 0 && y < in.H && x >= 0 && x < in.W);
+      const long long pix = ((long long)img * in.H + y) * in.W + x;
+      for (int ci = 0; ci < cin; ++ci) {
+        float v = 0.0f;
+        if (inb) {
+          if (U8) v = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[pix * in.ld + ci]];
+          else v = reinterpret_cast<const float*>(in.ptr)[pix * in.ld + ci];
+        }
+        const float4* wrow = reinterpret_cast<const float4*>(s_w + ((kh * a.ksize + kw) * cin + ci) * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 w4 = wrow[j4];
+          acc[j4 * 4 + 0] = fmaf(v, w4.x, acc[j4 * 4 + 0]);
+          acc[j4 * 4 + 1] = fmaf(v, w4.y, acc[j4 * 4 + 1]);
+          acc[j4 * 4 + 2] = fmaf(v, w4.z, acc[j4 * 4 + 2]);
+          acc[j4 * 4 + 3] = fmaf(v, w4.w, acc[j4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int co = min(c0 + j, a.cout - 1);
+    float yv = acc[j] * a.scale[co] + a.shift[co];
+    if (a.leaky) yv = fmaxf(yv, 0.1f * yv);
+    f[j] = yv;
+  }
+  if (a.out_mode == OUT_PLAIN && !a.out_f32 && a.res == nullptr && c0 + 32 <= a.cout) {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)m * a.out_ld + c0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 pk;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+      __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+      __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+      pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+      *reinterpret_cast<uint4*>(op + g * 8) = pk;
+    }
+  } else {
+    for (int j = 0; j < 32; ++j) {
+      const int co = c0 + j;
+      if (co >= a.cout) break;
+      float yv = f[j];
+      if (a.res) yv += __bfloat162float(a.res[(long long)m * a.res_ld + co]);
+      store_out(a, m, co, yv);
+    }
+  }
+}
+
+// ---- plain CUDA-core conv on the packed bf16 operands: wt [cout_pad][taps*Cin] ----
+// one thread = one output pixel x 4 output channels
+__global__ void __launch_bounds__(256) conv_simt_kernel(const InView in, const __nv_bfloat16* __restrict__ wt, const ConvArgs a) {
+  const int groups = (a.cout + 3) >> 2;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)a.M * groups) return;
+  const int m = (int)(gid / groups);
+  const int co0 = (int)(gid - (long long)m * groups) * 4;
+  const int hw = a.Ho * a.Wo;
+  const int img = m / hw, rem = m - img * hw;
+  const int p = rem / a.Wo, q = rem - p * a.Wo;
+  const int K = a.taps * in.C;
+  const uint16_t* x = reinterpret_cast<const uint16_t*>(in.ptr);
+  const uint16_t* w = reinterpret_cast<const uint16_t*>(wt);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < a.ksize; ++kh) {
+    const int y = p * a.conv_stride + kh - a.pad;
+    if (y < 0 || y >= in.H) continue;
+    for (int kw = 0; kw < a.ksize; ++kw) {
+      const int xx = q * a.conv_stride + kw - a.pad;
+      if (xx < 0 || xx >= in.W) continue;
+      const uint16_t* xp = x + (((long long)img * in.H + y) * in.W + xx) * in.ld;
+      const int kbase = (kh * a.ksize + kw) * in.C;
+      for (int ci = 0; ci < in.C; ++ci) {
+        const float v = bf16_bits_to_f32(xp[ci]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, bf16_bits_to_f32(w[(long long)(co0 + j) * K + kbase + ci]), acc[j]);
+      }
+    }
+  }
+  for (int j = 0; j < 4; ++j) {
+    const int co = co0 + j;
+    if (co >= a.cout) break;
+    float yv = acc[j] * a.scale[co] + a.shift[co];
+    if (a.leaky) yv = fmaxf(yv, 0.1f * yv);
+    if (a.res) yv += __bfloat162float(a.res[(long long)m * a.res_ld + co]);
+    store_out(a, m, co, yv);
+  }
+}
+
+// ---- 2x2/2 max pool, 8 channels (16 B) per thread ----
+__global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16* __restrict__ in, int in_ld, int H, int W, int C,
+                                                       __nv_bfloat16* __restrict__ out, int out_ld, long long total_vec) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total_vec) return;
+  const int cv = C >> 3;
+  const int c8 = (int)(gid % cv);
+  const long long opix = gid / cv;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int q = (int)(opix % Wo);
+  const long long t = opix / Wo;
+  const int p = (int)(t % Ho);
+  const long long img = t / Ho;
+  const __nv_bfloat16* b = in + ((img * H + 2 * p) * W + 2 * q) * in_ld + c8 * 8;
+  const uint4 v00 = *reinterpret_cast<const uint4*>(b);
+  const uint4 v01 = *reinterpret_cast<const uint4*>(b + in_ld);
+  const uint4 v10 = *reinterpret_cast<const uint4*>(b + (long long)W * in_ld);
+  const uint4 v11 = *reinterpret_cast<const uint4*>(b + (long long)W * in_ld + in_ld);
+  uint4 r;
+  const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&v00);
+  const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&v01);
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&v10);
+  const __nv_bfloat162* a3 = reinterpret_cast<const __nv_bfloat162*>(&v11);
+  __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(__hmax2(a0[i], a1[i]), __hmax2(a2[i], a3[i]));
+  *reinterpret_cast<uint4*>(out + opix * out_ld + c8 * 8) = r;
+}
+
+// ---- generic element-wise fallbacks (bf16, one element per thread; not on the v2/v3 hot path) ----
+__global__ void add_kernel(const __nv_bfloat16* a, int a_ld, const __nv_bfloat16* b, int b_ld, __nv_bfloat16* out, int out_ld,
+                           int C, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const long long pix = gid / C;
+  const int c = (int)(gid - pix * C);
+  out[pix * out_ld + c] = __float2bfloat16_rn(__bfloat162float(a[pix * a_ld + c]) + __bfloat162float(b[pix * b_ld + c]));
+}
+__global__ void copy_channels_kernel(const __nv_bfloat16* in, int in_ld, __nv_bfloat16* out, int out_ld, int C, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const long long pix = gid / C;
+  const int c = (int)(gid - pix * C);
+  out[pix * out_ld + c] = in[pix * in_ld + c];
+}
+__global__ void upsample_kernel(const __nv_bfloat16* in, int in_ld, int H, int W, int C, int s, __nv_bfloat16* out, int out_ld,
+                                long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid % C);
+  long long t = gid / C;
+  const int x = (int)(t % (W * s)); t /= (W * s);
+  const int y = (int)(t % (H * s));
+  const long long img = t / (H * s);
+  out[((img * H * s + y) * (W * s) + x) * out_ld + c] = in[((img * H + y / s) * W + x / s) * in_ld + c];
+}
+__global__ void reorg_kernel(const __nv_bfloat16* in, int in_ld, int H, int W, int C, int s, __nv_bfloat16* out, int out_ld,
+                             long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid % C);
+  long long t = gid / C;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H);
+  const long long img = t / H;
+  const int oc = ((y % s) * s + (x % s)) * C + c;
+  out[((img * (H / s) + y / s) * (W / s) + x / s) * out_ld + oc] = in[((img * H + y) * W + x) * in_ld + c];
+}
+
+// ---- layout conversion for parity reads ----
+// head view (fp32, ld >= na*box_len) -> reference rows [n, rows_total, box_len] at row_begin
+__global__ void gather_head_kernel(const float* head, int ld, int cells, int na, int box_len, int row_begin, int rows_total,
+                                   float* out, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int k = (int)(gid % box_len);
+  long long t = gid / box_len;
+  const int anc = (int)(t % na); t /= na;
+  const int cell = (int)(t % cells);
+  const long long img = t / cells;
+  out[(img * rows_total + row_begin + (long long)cell * na + anc) * box_len + k] = head[(img * cells + cell) * ld + anc * box_len + k];
+}
+// any view -> dense NHWC fp32
+__global__ void read_view_kernel(const void* in, int ld, int C, int is_f32, float* out, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const long long pix = gid / C;
+  const int c = (int)(gid - pix * C);
+  out[gid] = is_f32 ? reinterpret_cast<const float*>(in)[pix * ld + c]
+                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[pix * ld + c]);
+}
+
+}  // namespace yb

@@ -1,0 +1,383 @@
+// conv_tc.cuh -- NHWC bf16 implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA (sm_100a only).
+//
+// Replaces tf.layers.conv2d + batch_normalization + leaky_relu (+ the shortcut add, the route
+// concat, the x2 nearest upsample and the space-to-depth reorg that follow it) of the reference's
+// net/layers.py:17-67,84-116 with ONE kernel per conv:
+//
+//   D[m, co] = sum_{kh,kw,ci} X[n, p*s + kh - pad, q*s + kw - pad, ci] * Wt[co, (kh,kw,ci)]      m = (n,p,q)
+//   Y = act(D * scale[co] + shift[co]) (+ residual[m, co])      -> bf16 (or fp32 for the heads)
+//
+// GEMM view: M = N*Ho*Wo pixels (tile 128 = the 128 TMEM lanes), N = Cout (tile BN = TMEM columns),
+// K = k*k*Cin walked as (tap, 64-channel block).  Per K step the producer warp issues
+//   * A: one TMA load of 128 pixels x BK channels.  1x1 convs use a tiled 2-D map over [pixels, C];
+//        3x3 convs use an IM2COL map over (C,W,H,N): the hardware walks 128 output pixels across
+//        rows and images from the tile's first pixel, applies the tap offset and the conv stride and
+//        zero-fills the padding halo -- the reference's tf.pad/"SAME" costs nothing.
+//   * B: one tiled TMA load of BN x BK weights (K-major, packed [Cout_pad][k*k*Cin] at load time).
+// Both land in 128B-swizzled (64B for Cin=32) K-major shared memory, exactly the canonical UMMA
+// operand layout, so a single elected thread issues BK/16 tcgen05.mma (M=128, N=BN, K=16) per step
+// with fp32 accumulation in TMEM.  tcgen05.commit releases smem stages / publishes the accumulator
+// through mbarriers; four epilogue warps read their TMEM lane quarter with tcgen05.ld and apply the
+// whole epilogue in registers before storing straight to the consumer's buffer (concat slices,
+// upsample replicas and reorg scatter are just different store addresses).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yb {
+
+enum OutMode { OUT_PLAIN = 0, OUT_UPSAMPLE2 = 1, OUT_REORG2 = 2 };
+
+struct ConvArgs {
+  int M;              // valid output pixels = n * Ho * Wo
+  int Ho, Wo;         // output spatial size
+  int cout;           // real output channels
+  int taps;           // ksize*ksize
+  int ksize;
+  int kc_blocks;      // Cin / BK
+  int conv_stride;    // 1 or 2
+  int pad;            // low-side padding ((k-1)/2)
+  int im2col;         // 1: A through the im2col map; 0: tiled [pixels, C] map (1x1 stride 1)
+  const float* scale; // [cout_pad]
+  const float* shift; // [cout_pad]
+  int leaky;
+  const __nv_bfloat16* res;  // residual (shortcut) or nullptr; pixel stride res_ld, already channel-offset
+  int res_ld;
+  void* out;          // already channel-offset
+  int out_ld;         // elements per output pixel
+  int out_f32;        // 1: float32 store (heads), 0: bf16
+  int out_mode;       // OutMode
+};
+
+// ----------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\t"
+      "elect.sync R|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (quarter*32 + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 8 rows * row bytes) | [46,48) version = 1 (sm_100)
+//   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint32_t row_bytes = BK * 2;
+  constexpr uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
+  constexpr uint64_t sbo = (8u * row_bytes) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6)=1, A bf16 [7,10)=1,
+// B bf16 [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int BN, int BK, int STAGES>
+struct ConvTcSmem {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full, tmem ptr, then scale/shift staging
+  static constexpr int SS_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8;
+  static constexpr int TOTAL = SS_OFFSET + 2 * BN * 4 + 1024;  // + slack for manual 1024B alignment
+};
+
+constexpr int CONV_TC_THREADS = 192;  // warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2-5 epilogue
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(CONV_TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
+               const int n_tiles_n) {
+  using L = ConvTcSmem<BN, BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFFSET);
+  float* s_shift = s_scale + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x % n_tiles_n;
+  const int tile_m = blockIdx.x / n_tiles_n;
+  const int m0 = tile_m * 128;
+  const int n0 = tile_n * BN;
+  const int num_k = a.taps * a.kc_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<BN>(tmem_ptr_smem);
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      s_scale[i] = a.scale[n0 + i];
+      s_shift[i] = a.shift[n0 + i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int img = 0, p0 = 0, q0 = 0;
+      if (a.im2col) {
+        const int hw = a.Ho * a.Wo;
+        img = m0 / hw;
+        const int rem = m0 - img * hw;
+        p0 = rem / a.Wo;
+        q0 = rem - p0 * a.Wo;
+      }
+      const int base_w = q0 * a.conv_stride - a.pad;
+      const int base_h = p0 * a.conv_stride - a.pad;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        const int tap = kb / a.kc_blocks;
+        const int cb = kb - tap * a.kc_blocks;
+        if (a.im2col) {
+          const int kh = tap / a.ksize;
+          const int kw = tap - kh * a.ksize;
+          tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+        } else {
+          tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+        }
+        tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc<BN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_k; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint64_t da = make_kmajor_desc<BK>(sa);
+        const uint64_t db = make_kmajor_desc<BK>(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);                   // frees this smem stage when the MMAs retire
+        if (kb == num_k - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ------------------------------ epilogue (4 warps, one TMEM lane quarter each) ------------------------------
+    const int quarter = warp & 3;
+    const int m = m0 + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool valid = m < a.M;
+    // destination pixel(s)
+    long long opix[4];
+    int n_dst = 1;
+    int ch_extra = 0;
+    if (a.out_mode == OUT_PLAIN) {
+      opix[0] = m;
+    } else {
+      const int hw = a.Ho * a.Wo;
+      const int img = m / hw;
+      const int rem = m - img * hw;
+      const int p = rem / a.Wo;
+      const int q = rem - p * a.Wo;
+      if (a.out_mode == OUT_UPSAMPLE2) {
+        const long long W2 = 2 * a.Wo;
+        const long long base = ((long long)img * 2 * a.Ho + 2 * p) * W2 + 2 * q;
+        opix[0] = base; opix[1] = base + 1; opix[2] = base + W2; opix[3] = base + W2 + 1;
+        n_dst = 4;
+      } else {  // OUT_REORG2: out[n, p/2, q/2, ((p%2)*2 + q%2)*cout + c]
+        opix[0] = ((long long)img * (a.Ho >> 1) + (p >> 1)) * (a.Wo >> 1) + (q >> 1);
+        ch_extra = ((p & 1) * 2 + (q & 1)) * a.cout;
+      }
+    }
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), v);
+      tmem_ld_wait();
+      const int cbase = n0 + chunk * 32;  // first output channel of this chunk
+      if (valid && cbase < a.cout) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float y = __uint_as_float(v[j]) * s_scale[chunk * 32 + j] + s_shift[chunk * 32 + j];
+          if (a.leaky) y = fmaxf(y, 0.1f * y);
+          f[j] = y;
+        }
+        if (a.res != nullptr) {
+          const __nv_bfloat16* rp = a.res + (long long)m * a.res_ld + cbase;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (cbase + g * 8 < a.cout) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rp + g * 8);
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+              }
+            }
+          }
+        }
+        if (a.out_f32) {
+          float* op = reinterpret_cast<float*>(a.out) + opix[0] * a.out_ld + cbase;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (cbase + g * 4 < a.out_ld)  // head buffers are padded to a multiple of 4 channels
+              *reinterpret_cast<float4*>(op + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+          }
+        } else {
+          uint4 pk[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+            pk[g].x = *reinterpret_cast<uint32_t*>(&b0);
+            pk[g].y = *reinterpret_cast<uint32_t*>(&b1);
+            pk[g].z = *reinterpret_cast<uint32_t*>(&b2);
+            pk[g].w = *reinterpret_cast<uint32_t*>(&b3);
+          }
+          for (int d = 0; d < n_dst; ++d) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + opix[d] * a.out_ld + ch_extra + cbase;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (cbase + g * 8 < a.cout) *reinterpret_cast<uint4*>(op + g * 8) = pk[g];
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+}  // namespace yb

@@ -1,0 +1,1147 @@
+// engine.cu -- libyolo_b200.so: plan compiler, activation arena, weight packing, launch sequencing and
+// the C ABI declared in include/yolo_b200.h.  Host code only orchestrates; all arithmetic of the TEST
+// hot path (net/yolo.py:83,86 of the reference) runs in the kernels of conv_tc.cuh, aux_kernels.cuh
+// and post.cuh.  There is no CPU fallback: every compute entry point fails with YB_ERR_CUDA when no
+// CUDA device is usable.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/yolo_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_tc.cuh"
+#include "post.cuh"
+
+namespace yb {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define YB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      cudaGetLastError();                                                                          \
+      return fail(YB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                              \
+  } while (0)
+#define YB_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != YB_OK) return _r; \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// driver entry points for tensor-map encoding (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_EncodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_EncodeTiled g_encode_tiled = nullptr;
+static PFN_EncodeIm2col g_encode_im2col = nullptr;
+
+static int load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return YB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  YB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+  g_encode_tiled = (PFN_EncodeTiled)fn;
+  fn = nullptr;
+  YB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(YB_ERR_CUDA, "cuTensorMapEncodeIm2col not available in this driver");
+  g_encode_im2col = (PFN_EncodeIm2col)fn;
+  return YB_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
+
+// [rows, cols] bf16 row-major with row pitch ld (elements); box = box_rows x bk
+static int make_tiled_map(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_rows, int bk) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%d ld=%d box=%dx%d", (int)r, rows, cols, ld, box_rows, bk);
+  return YB_OK;
+}
+
+// activation [N,H,W,C] bf16 (pixel pitch ld) as an im2col map: 128 output pixels x bk channels per load
+static int make_im2col_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int ld, int ksize, int stride,
+                           int pad_lo, int bk) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  const int pad_hi = (ksize - 1) - pad_lo;
+  int lower[2] = {-pad_lo, -pad_lo};                               // {W, H}: offset of the first window's origin
+  int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};     // far corner: last window origin relative to the edge
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                               (cuuint32_t)bk, 128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d): N=%d H=%d W=%d C=%d ld=%d k=%d s=%d", (int)r, N, H, W, C, ld, ksize, stride);
+  // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1 set a
+  // descriptor bit that breaks im2col loads of tensors smaller than 128 KiB.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  const unsigned long long bytes = (unsigned long long)N * H * W * ld * 2;
+  if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return YB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing context (decode + sort + NMS), shared by the engine and the stand-alone yb_post_* API
+// ------------------------------------------------------------------------------------------------
+struct PostCtx {
+  int max_batch = 0, rows = 0, rows_pow2 = 0, box_len = 0, n_scales = 0, v2 = 0;
+  ScaleDesc scales[POST_MAX_SCALES];
+  float *prob = nullptr, *x = nullptr, *y = nullptr;
+  double *w = nullptr, *h = nullptr;
+  int* cls = nullptr;
+  unsigned long long* keys = nullptr;
+  void* sorted_boxes = nullptr;
+  int* sorted_cls = nullptr;
+  unsigned char* flags = nullptr;
+  int *order = nullptr, *n_keep = nullptr, *n_cand = nullptr;
+  DetOut* dets = nullptr;
+  size_t dets_cap = 0;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  bool smem_set = false;
+
+  int alloc(int max_batch_, int rows_, int box_len_, int v2_) {
+    max_batch = max_batch_; rows = rows_; box_len = box_len_; v2 = v2_;
+    rows_pow2 = 1;
+    while (rows_pow2 < rows) rows_pow2 <<= 1;
+    const size_t nr = (size_t)max_batch * rows;
+    YB_CUDA(cudaMalloc(&prob, nr * 4)); YB_CUDA(cudaMalloc(&x, nr * 4)); YB_CUDA(cudaMalloc(&y, nr * 4));
+    YB_CUDA(cudaMalloc(&w, nr * 8)); YB_CUDA(cudaMalloc(&h, nr * 8)); YB_CUDA(cudaMalloc(&cls, nr * 4));
+    if (rows_pow2 > NMS_SMEM_KEYS) YB_CUDA(cudaMalloc(&keys, (size_t)max_batch * rows_pow2 * 8));
+    YB_CUDA(cudaMalloc(&sorted_boxes, nr * sizeof(BoxC<double>)));
+    YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
+    YB_CUDA(cudaMalloc(&order, nr * 4));
+    YB_CUDA(cudaMalloc(&n_keep, (size_t)max_batch * 4)); YB_CUDA(cudaMalloc(&n_cand, (size_t)max_batch * 4));
+    dets_cap = nr;
+    YB_CUDA(cudaMalloc(&dets, nr * sizeof(DetOut)));
+    for (int i = 0; i < 3; ++i) YB_CUDA(cudaEventCreate(&ev[i]));
+    return YB_OK;
+  }
+  void release() {
+    cudaFree(prob); cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(h); cudaFree(cls); cudaFree(keys);
+    cudaFree(sorted_boxes); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
+    cudaFree(dets);
+    for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+  }
+
+  // scales[] must carry base/img_stride/cell_stride for this call
+  int decode(cudaStream_t st, const ScaleDesc* sc, int n, float thr) {
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_scales; ++i) a.sc[i] = sc[i];
+    a.n_scales = n_scales; a.rows = rows; a.box_len = box_len; a.n_images = n; a.v2 = v2; a.thr = thr;
+    a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
+    const long long warps = (long long)n * rows;
+    const int blocks = ceil_div(warps * 32, 256);
+    decode_kernel<<<blocks, 256, 0, st>>>(a);
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
+
+  template <typename T, bool XY64, bool WH64>
+  int nms_launch(cudaStream_t st, int n, const NmsArgs& a) {
+    auto kern = sort_nms_kernel<T, XY64, WH64>;
+    const int smem = NMS_SMEM_KEYS * 8;
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<n, NMS_THREADS, smem, st>>>(a);
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
+
+  NmsArgs nms_args(double thr, int per_class) const {
+    NmsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = rows; a.per_class = per_class; a.thr = thr;
+    a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
+    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_cls = sorted_cls;
+    a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;
+    return a;
+  }
+
+  // engine path: float32 x,y + float64 w,h, IoU in float64 (the reference's dtypes)
+  int nms(cudaStream_t st, int n, double iou_thr, int mode) {
+    YB_CUDA(cudaMemsetAsync(flags, 0, (size_t)n * rows, st));
+    return nms_launch<double, false, true>(st, n, nms_args(iou_thr, mode == YB_NMS_PER_CLASS));
+  }
+
+  int gather(cudaStream_t st, int n, int max_per_image) {
+    dim3 grid(ceil_div(max_per_image, 128), n);
+    gather_dets_kernel<<<grid, 128, 0, st>>>(rows, max_per_image, order, n_keep, prob, x, y, w, h, cls, dets);
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct Shape { int h = 0, w = 0, c = 0; };
+struct View {
+  int buf = -1;       // index into bufs, -2 = network input, -1 = none (fused away / not a tensor)
+  int coff = 0, ld = 0, h = 0, w = 0, c = 0;
+  bool f32 = false;
+};
+struct Buf {
+  size_t bytes = 0, off = 0;
+  int first = INT_MAX, last = -1;
+  bool keep = false;
+};
+enum OpKind { OP_CONV = 0, OP_MAXPOOL, OP_ADD, OP_UPSAMPLE, OP_REORG, OP_COPY };
+enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2 };
+
+struct Op {
+  int kind = 0, layer = -1;
+  View in, in2, out;
+  // conv
+  int cout = 0, cout_pad = 0, cin = 0, ksize = 0, stride = 1, pad = 0, leaky = 0, has_res = 0, out_mode = 0;
+  int Ho = 0, Wo = 0, path = PATH_TC, bn_tile = 0, bk = 0, stages = 0;
+  __nv_bfloat16* d_wt = nullptr;
+  float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+  alignas(64) CUtensorMap tmA, tmB;
+  // generic
+  int factor = 0;
+};
+
+struct Head {
+  int yolo_layer = -1, conv_layer = -1;
+  View view;
+  int h = 0, w = 0, na = 0, row_begin = 0;
+  float anchors[2 * YB_MAX_ANCHORS];
+};
+
+}  // namespace yb
+
+using namespace yb;
+
+struct yb_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<yb_layer> plan;
+  int H = 0, W = 0, C = 0, max_batch = 0, decode_mode = 0, num_classes = 0;
+  bool keep_all = false;
+  int bn_max = 128;
+  std::vector<Shape> shape;
+  std::vector<View> view;
+  std::vector<Buf> bufs;
+  std::vector<Op> ops;
+  std::vector<Head> heads;
+  int rows = 0, box_len = 0;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  void* input_dev = nullptr;      // staging for host images (max_batch*H*W*C floats)
+  const void* cur_input = nullptr;
+  int cur_input_dtype = YB_F32;
+  float* d_u8_lut = nullptr;
+  float* scratch_f32 = nullptr;   // read_output / read_layer staging
+  size_t scratch_floats = 0;
+  PostCtx post;
+  bool weights_loaded = false;
+  int last_n = 0;
+  bool detected = false;
+  int conv_impl = 0;
+  int fwd_launches = 0, det_launches = 0;
+};
+
+namespace yb {
+
+static void* view_ptr(const yb_engine* e, const View& v) {
+  if (v.buf == -2) return const_cast<void*>(e->cur_input);
+  if (v.buf < 0) return nullptr;
+  return e->arena + e->bufs[v.buf].off + (size_t)v.coff * (v.f32 ? 4 : 2);
+}
+
+template <int BN, int BK, int ST>
+static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
+  using L = ConvTcSmem<BN, BK, ST>;
+  auto kern = conv_tc_kernel<BN, BK, ST>;
+  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  const int tiles_m = ceil_div(a.M, 128);
+  const int tiles_n = op.cout_pad / BN;
+  kern<<<tiles_m * tiles_n, CONV_TC_THREADS, L::TOTAL, st>>>(op.tmA, op.tmB, a, tiles_n);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+static int stages_for(int bn, int bk) {
+  // env override for tuning; defaults keep two CTAs resident per SM where the tile allows it
+  const char* s = getenv("YB_STAGES");
+  if (s && atoi(s) > 0) return atoi(s);
+  if (bn == 256) return 4;
+  if (bn == 128 && bk == 64) return 3;
+  return 4;
+}
+
+static int dispatch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
+#define YB_CASE(BN_, BK_, ST_) \
+  if (op.bn_tile == BN_ && op.bk == BK_ && op.stages == ST_) return launch_conv_tc<BN_, BK_, ST_>(st, op, a);
+  YB_CASE(256, 64, 4) YB_CASE(256, 64, 3)
+  YB_CASE(128, 64, 3) YB_CASE(128, 64, 4) YB_CASE(128, 64, 6)
+  YB_CASE(64, 64, 4) YB_CASE(64, 64, 6) YB_CASE(64, 64, 3)
+  YB_CASE(32, 64, 4) YB_CASE(32, 64, 6) YB_CASE(32, 64, 3)
+  YB_CASE(128, 32, 4) YB_CASE(128, 32, 6) YB_CASE(128, 32, 3)
+  YB_CASE(64, 32, 4) YB_CASE(64, 32, 6) YB_CASE(64, 32, 3)
+  YB_CASE(32, 32, 4) YB_CASE(32, 32, 6) YB_CASE(32, 32, 3)
+#undef YB_CASE
+  return fail(YB_ERR_INVALID, "no tcgen05 conv instantiation for BN=%d BK=%d stages=%d", op.bn_tile, op.bk, op.stages);
+}
+
+static int run_op(yb_engine* e, Op& op, int n) {
+  cudaStream_t st = e->stream;
+  if (op.kind == OP_CONV) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = n * op.Ho * op.Wo; a.Ho = op.Ho; a.Wo = op.Wo; a.cout = op.cout; a.taps = op.ksize * op.ksize; a.ksize = op.ksize;
+    a.conv_stride = op.stride; a.pad = op.pad; a.scale = op.d_scale; a.shift = op.d_shift; a.leaky = op.leaky;
+    a.res = op.has_res ? reinterpret_cast<const __nv_bfloat16*>(view_ptr(e, op.in2)) : nullptr;
+    a.res_ld = op.in2.ld;
+    a.out = view_ptr(e, op.out); a.out_ld = op.out.ld; a.out_f32 = op.out.f32 ? 1 : 0; a.out_mode = op.out_mode;
+    InView in{view_ptr(e, op.in), op.in.ld, op.in.h, op.in.w, op.in.c};
+    int path = op.path;
+    if (path == PATH_TC && e->conv_impl == 1) path = PATH_SIMT;
+    if (path == PATH_TC) {
+      a.kc_blocks = op.cin / op.bk;
+      a.im2col = !(op.ksize == 1 && op.stride == 1);
+      YB_TRY(dispatch_conv_tc(st, op, a));
+    } else if (path == PATH_DIRECT) {
+      const int smem = a.taps * op.cin * 32 * 4;
+      dim3 grid(ceil_div(a.M, 128), ceil_div(op.cout, 32));
+      if (e->cur_input_dtype == YB_U8 && op.in.buf == -2)
+        conv_direct_kernel<true><<<grid, 128, smem, st>>>(in, op.d_wt32, a, e->d_u8_lut);
+      else
+        conv_direct_kernel<false><<<grid, 128, smem, st>>>(in, op.d_wt32, a, e->d_u8_lut);
+      YB_CUDA(cudaGetLastError());
+    } else {
+      const long long total = (long long)a.M * ((op.cout + 3) / 4);
+      conv_simt_kernel<<<ceil_div(total, 256), 256, 0, st>>>(in, op.d_wt, a);
+      YB_CUDA(cudaGetLastError());
+    }
+    return YB_OK;
+  }
+  const __nv_bfloat16* ip = reinterpret_cast<const __nv_bfloat16*>(view_ptr(e, op.in));
+  __nv_bfloat16* opn = reinterpret_cast<__nv_bfloat16*>(view_ptr(e, op.out));
+  if (op.kind == OP_MAXPOOL) {
+    const long long total = (long long)n * op.out.h * op.out.w * (op.in.c / 8);
+    maxpool2_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ip, op.in.ld, op.in.h, op.in.w, op.in.c, opn, op.out.ld, total);
+  } else if (op.kind == OP_ADD) {
+    const long long total = (long long)n * op.out.h * op.out.w * op.out.c;
+    add_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ip, op.in.ld, reinterpret_cast<const __nv_bfloat16*>(view_ptr(e, op.in2)),
+                                                      op.in2.ld, opn, op.out.ld, op.out.c, total);
+  } else if (op.kind == OP_UPSAMPLE) {
+    const long long total = (long long)n * op.out.h * op.out.w * op.out.c;
+    upsample_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ip, op.in.ld, op.in.h, op.in.w, op.in.c, op.factor, opn, op.out.ld, total);
+  } else if (op.kind == OP_REORG) {
+    const long long total = (long long)n * op.in.h * op.in.w * op.in.c;
+    reorg_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ip, op.in.ld, op.in.h, op.in.w, op.in.c, op.factor, opn, op.out.ld, total);
+  } else if (op.kind == OP_COPY) {
+    const long long total = (long long)n * op.out.h * op.out.w * op.in.c;
+    copy_channels_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ip, op.in.ld, opn, op.out.ld, op.in.c, total);
+  }
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// ---- plan compilation ----
+static int compile_plan(yb_engine* e) {
+  const int n = (int)e->plan.size();
+  const std::vector<yb_layer>& P = e->plan;
+  e->shape.assign(n, Shape());
+  e->view.assign(n, View());
+  std::vector<std::vector<int>> consumers(n);
+  if (n < 2 || P[0].kind != YB_INPUT) return fail(YB_ERR_INVALID, "plan must start with an input layer");
+  for (int i = 0; i < n; ++i) {
+    const yb_layer& l = P[i];
+    if (l.n_src < 0 || l.n_src > YB_MAX_SRC) return fail(YB_ERR_INVALID, "layer %d: bad n_src", i);
+    for (int s = 0; s < l.n_src; ++s) {
+      if (l.src[s] < 0 || l.src[s] >= i) return fail(YB_ERR_INVALID, "layer %d: source %d is not an earlier layer", i, l.src[s]);
+      consumers[l.src[s]].push_back(i);
+    }
+    Shape& sh = e->shape[i];
+    auto S = [&](int k) -> const Shape& { return e->shape[l.src[k]]; };
+    switch (l.kind) {
+      case YB_INPUT: sh.h = e->H; sh.w = e->W; sh.c = e->C; break;
+      case YB_CONV:
+        if (l.n_src != 1 || l.filters <= 0 || l.ksize <= 0 || l.stride <= 0) return fail(YB_ERR_INVALID, "layer %d: bad conv", i);
+        if (l.ksize % 2 == 0) return fail(YB_ERR_INVALID, "layer %d: even conv kernels are not supported", i);
+        sh.h = l.stride > 1 ? (S(0).h - 1) / l.stride + 1 : S(0).h;
+        sh.w = l.stride > 1 ? (S(0).w - 1) / l.stride + 1 : S(0).w;
+        sh.c = l.filters;
+        break;
+      case YB_MAXPOOL:
+        if (l.n_src != 1 || l.ksize != 2 || l.stride != 2 || (S(0).h & 1) || (S(0).w & 1) || (S(0).c & 7))
+          return fail(YB_ERR_INVALID, "layer %d: only 2x2/2 max pool on even maps with C%%8==0 is supported", i);
+        sh.h = S(0).h / 2; sh.w = S(0).w / 2; sh.c = S(0).c;
+        break;
+      case YB_ROUTE:
+        if (l.n_src < 1) return fail(YB_ERR_INVALID, "layer %d: route without sources", i);
+        sh.h = S(0).h; sh.w = S(0).w; sh.c = 0;
+        for (int s = 0; s < l.n_src; ++s) {
+          if (S(s).h != sh.h || S(s).w != sh.w) return fail(YB_ERR_INVALID, "layer %d: route inputs differ in size", i);
+          sh.c += S(s).c;
+        }
+        break;
+      case YB_REORG:
+        if (l.n_src != 1 || l.stride < 1 || S(0).h % l.stride || S(0).w % l.stride) return fail(YB_ERR_INVALID, "layer %d: bad reorg", i);
+        sh.h = S(0).h / l.stride; sh.w = S(0).w / l.stride; sh.c = S(0).c * l.stride * l.stride;
+        break;
+      case YB_SHORTCUT:
+        if (l.n_src != 2 || S(0).h != S(1).h || S(0).w != S(1).w || S(0).c != S(1).c) return fail(YB_ERR_INVALID, "layer %d: bad shortcut", i);
+        sh = S(0);
+        break;
+      case YB_UPSAMPLE:
+        if (l.n_src != 1 || l.stride < 1) return fail(YB_ERR_INVALID, "layer %d: bad upsample", i);
+        sh.h = S(0).h * l.stride; sh.w = S(0).w * l.stride; sh.c = S(0).c;
+        break;
+      case YB_YOLO:
+        if (l.n_src != 1 || l.n_anchors < 1 || l.n_anchors > YB_MAX_ANCHORS) return fail(YB_ERR_INVALID, "layer %d: bad yolo layer", i);
+        if (P[l.src[0]].kind != YB_CONV) return fail(YB_ERR_INVALID, "layer %d: a yolo layer must follow a conv", i);
+        if (S(0).c != l.n_anchors * (5 + e->num_classes))
+          return fail(YB_ERR_INVALID, "layer %d: head has %d channels, expected %d", i, S(0).c, l.n_anchors * (5 + e->num_classes));
+        sh = S(0);
+        break;
+      case YB_DETECTION: sh = Shape(); break;
+      default: return fail(YB_ERR_INVALID, "layer %d: unknown kind %d", i, l.kind);
+    }
+  }
+  // --- fusion decisions ---
+  std::vector<int> absorbed_into(n, -1);   // conv i writes directly into the view of layer absorbed_into[i]
+  std::vector<int> res_src(n, -1);
+  std::vector<int> out_mode(n, OUT_PLAIN);
+  std::vector<bool> is_head(n, false);
+  for (int i = 0; i < n; ++i) {
+    if (P[i].kind != YB_CONV) continue;
+    const std::vector<int>& cs = consumers[i];
+    bool all_yolo = !cs.empty();
+    for (int c : cs) all_yolo = all_yolo && P[c].kind == YB_YOLO;
+    if (all_yolo || (cs.empty() && i == n - 1)) { is_head[i] = true; continue; }
+    if (cs.size() != 1) continue;
+    const int j = cs[0];
+    const bool tc_ok = true;
+    if (P[j].kind == YB_SHORTCUT && P[j].src[0] == i && P[j].src[1] != i && tc_ok) { absorbed_into[i] = j; res_src[i] = P[j].src[1]; }
+    else if (P[j].kind == YB_UPSAMPLE && P[j].stride == 2) { absorbed_into[i] = j; out_mode[i] = OUT_UPSAMPLE2; }
+    else if (P[j].kind == YB_REORG && P[j].stride == 2 && (e->shape[i].h % 2 == 0) && (e->shape[i].w % 2 == 0)) { absorbed_into[i] = j; out_mode[i] = OUT_REORG2; }
+  }
+  std::vector<bool> absorbs(n, false);
+  for (int i = 0; i < n; ++i) if (absorbed_into[i] >= 0) absorbs[absorbed_into[i]] = true;
+  auto root_of = [&](int s) { while (P[s].kind == YB_ROUTE && P[s].n_src == 1) s = P[s].src[0]; return s; };
+  // --- concat placement ---
+  struct Place { int route = -1, coff = 0; };
+  std::vector<Place> placed(n);
+  for (int j = 0; j < n; ++j) {
+    if (P[j].kind != YB_ROUTE || P[j].n_src < 2) continue;
+    int coff = 0;
+    for (int s = 0; s < P[j].n_src; ++s) {
+      const int r = root_of(P[j].src[s]);
+      const int k = P[r].kind;
+      const bool placeable = (k == YB_CONV && absorbed_into[r] < 0 && !is_head[r]) || k == YB_MAXPOOL || k == YB_SHORTCUT ||
+                             k == YB_UPSAMPLE || k == YB_REORG;
+      if (placeable && placed[r].route < 0 && (coff % 8) == 0 && (e->shape[r].c % 8) == 0) { placed[r].route = j; placed[r].coff = coff; }
+      coff += e->shape[P[j].src[s]].c;
+    }
+  }
+  // --- views and buffers ---
+  auto new_buf = [&](const Shape& sh, int ld, bool f32) {
+    Buf b;
+    b.bytes = (size_t)e->max_batch * sh.h * sh.w * ld * (f32 ? 4 : 2);
+    b.keep = e->keep_all;
+    e->bufs.push_back(b);
+    return (int)e->bufs.size() - 1;
+  };
+  std::vector<int> route_buf(n, -1);
+  for (int j = 0; j < n; ++j)
+    if (P[j].kind == YB_ROUTE && P[j].n_src >= 2) route_buf[j] = new_buf(e->shape[j], round_up(e->shape[j].c, 8), false);
+  for (int i = 0; i < n; ++i) {
+    const Shape& sh = e->shape[i];
+    View v;
+    v.h = sh.h; v.w = sh.w; v.c = sh.c;
+    const int k = P[i].kind;
+    if (k == YB_INPUT) { v.buf = -2; v.ld = sh.c; v.f32 = true; }
+    else if (k == YB_DETECTION) { v.buf = -1; }
+    else if (k == YB_YOLO) { v = e->view[P[i].src[0]]; }
+    else if (k == YB_ROUTE && P[i].n_src == 1) { v = e->view[P[i].src[0]]; }
+    else if (k == YB_ROUTE) { v.buf = route_buf[i]; v.ld = round_up(sh.c, 8); v.coff = 0; }
+    else if (k == YB_CONV && absorbed_into[i] >= 0) { v.buf = -1; }
+    else if (placed[i].route >= 0) { v.buf = route_buf[placed[i].route]; v.ld = round_up(e->shape[placed[i].route].c, 8); v.coff = placed[i].coff; }
+    else if (k == YB_CONV && is_head[i]) { v.f32 = true; v.ld = round_up(sh.c, 4); v.buf = new_buf(sh, v.ld, true); e->bufs[v.buf].keep = true; }
+    else { v.ld = round_up(sh.c, 8); v.buf = new_buf(sh, v.ld, false); }
+    e->view[i] = v;
+  }
+  // --- ops ---
+  auto touch = [&](const View& v, int op_idx, bool write) {
+    if (v.buf < 0) return;
+    Buf& b = e->bufs[v.buf];
+    if (write) b.first = std::min(b.first, op_idx);
+    b.first = std::min(b.first, op_idx);
+    b.last = std::max(b.last, op_idx);
+  };
+  for (int i = 0; i < n; ++i) {
+    const yb_layer& l = P[i];
+    Op op;
+    op.layer = i;
+    bool emit = false;
+    if (l.kind == YB_CONV) {
+      const int dst = absorbed_into[i] >= 0 ? absorbed_into[i] : i;
+      op.kind = OP_CONV;
+      op.in = e->view[l.src[0]];
+      if (op.in.buf == -1) return fail(YB_ERR_INVALID, "layer %d: input %d was fused away", i, l.src[0]);
+      op.out = e->view[dst];
+      op.cin = e->shape[l.src[0]].c; op.cout = l.filters; op.ksize = l.ksize; op.stride = l.stride;
+      op.pad = (l.ksize - 1) / 2; op.leaky = l.leaky; op.out_mode = out_mode[i];
+      op.Ho = e->shape[i].h; op.Wo = e->shape[i].w;
+      if (res_src[i] >= 0) { op.has_res = 1; op.in2 = e->view[res_src[i]]; if (op.in2.buf == -1 || op.in2.f32) return fail(YB_ERR_INVALID, "layer %d: bad residual source", i); }
+      const bool in_bf16 = !op.in.f32;
+      const bool tma_ok = in_bf16 && (op.cin % 32 == 0) && (op.in.ld % 8 == 0) && (op.in.coff % 8 == 0) &&
+                          (l.ksize == 1 || l.ksize == 3) && (l.stride == 1 || l.stride == 2) &&
+                          (op.out.f32 || (op.cout % 8 == 0 && op.out.ld % 8 == 0 && op.out.coff % 8 == 0)) &&
+                          (!op.has_res || (op.in2.ld % 8 == 0 && op.in2.coff % 8 == 0));
+      if (op.in.f32 || op.in.buf == -2) {
+        if (op.cin > 8) return fail(YB_ERR_INVALID, "layer %d: fp32 conv input with %d channels is not supported", i, op.cin);
+        op.path = PATH_DIRECT;
+      } else if (tma_ok) {
+        op.path = PATH_TC;
+        op.bk = (op.cin % 64 == 0) ? 64 : 32;
+        int bn = 32;
+        while (bn < e->bn_max && bn < op.cout) bn <<= 1;
+        if (op.bk == 32 && bn > 128) bn = 128;
+        op.bn_tile = bn;
+        op.stages = stages_for(bn, op.bk);
+      } else {
+        op.path = PATH_SIMT;
+      }
+      op.cout_pad = round_up(op.cout, op.path == PATH_TC ? op.bn_tile : 4);
+      emit = true;
+    } else if (l.kind == YB_MAXPOOL) {
+      op.kind = OP_MAXPOOL; op.in = e->view[l.src[0]]; op.out = e->view[i]; emit = true;
+      if (op.in.f32 || op.in.buf < 0) return fail(YB_ERR_INVALID, "layer %d: max pool needs a bf16 activation input", i);
+    } else if (l.kind == YB_SHORTCUT && !absorbs[i]) {
+      op.kind = OP_ADD; op.in = e->view[l.src[0]]; op.in2 = e->view[l.src[1]]; op.out = e->view[i]; emit = true;
+      if (op.in.buf < 0 || op.in2.buf < 0 || op.in.f32 || op.in2.f32) return fail(YB_ERR_INVALID, "layer %d: bad shortcut operands", i);
+    } else if (l.kind == YB_UPSAMPLE && !absorbs[i]) {
+      op.kind = OP_UPSAMPLE; op.in = e->view[l.src[0]]; op.out = e->view[i]; op.factor = l.stride; emit = true;
+      if (op.in.buf < 0 || op.in.f32) return fail(YB_ERR_INVALID, "layer %d: bad upsample operand", i);
+    } else if (l.kind == YB_REORG && !absorbs[i]) {
+      op.kind = OP_REORG; op.in = e->view[l.src[0]]; op.out = e->view[i]; op.factor = l.stride; emit = true;
+      if (op.in.buf < 0 || op.in.f32) return fail(YB_ERR_INVALID, "layer %d: bad reorg operand", i);
+    } else if (l.kind == YB_ROUTE && l.n_src >= 2) {
+      int coff = 0;
+      for (int s = 0; s < l.n_src; ++s) {
+        const int r = root_of(l.src[s]);
+        if (!(placed[r].route == i && placed[r].coff == coff)) {
+          Op cp;
+          cp.kind = OP_COPY; cp.layer = i; cp.in = e->view[l.src[s]]; cp.out = e->view[i];
+          cp.out.coff += coff; cp.out.c = cp.in.c;
+          if (cp.in.buf < 0 || cp.in.f32) return fail(YB_ERR_INVALID, "layer %d: cannot concatenate source %d", i, l.src[s]);
+          const int idx = (int)e->ops.size();
+          touch(cp.in, idx, false); touch(cp.out, idx, true);
+          e->ops.push_back(cp);
+        }
+        coff += e->shape[l.src[s]].c;
+      }
+    }
+    if (emit) {
+      const int idx = (int)e->ops.size();
+      touch(op.in, idx, false);
+      if (op.kind == OP_ADD || op.has_res) touch(op.in2, idx, false);
+      touch(op.out, idx, true);
+      e->ops.push_back(op);
+    }
+  }
+  // --- heads ---
+  int row = 0;
+  for (int i = 0; i < n; ++i) {
+    if (P[i].kind != YB_YOLO) continue;
+    Head hd;
+    hd.yolo_layer = i; hd.conv_layer = P[i].src[0]; hd.view = e->view[hd.conv_layer];
+    if (!hd.view.f32 || hd.view.buf < 0) return fail(YB_ERR_INVALID, "layer %d: yolo input must be a head conv consumed only by yolo layers", i);
+    hd.h = e->shape[i].h; hd.w = e->shape[i].w; hd.na = P[i].n_anchors; hd.row_begin = row;
+    memcpy(hd.anchors, P[i].anchors, sizeof(float) * 2 * hd.na);
+    row += hd.h * hd.w * hd.na;
+    e->heads.push_back(hd);
+  }
+  if (e->heads.empty()) return fail(YB_ERR_INVALID, "plan has no yolo layer (append one for YOLOv2)");
+  if ((int)e->heads.size() > POST_MAX_SCALES) return fail(YB_ERR_INVALID, "too many yolo layers");
+  e->rows = row;
+  e->box_len = 5 + e->num_classes;
+  if (e->rows > 65536 * 16) return fail(YB_ERR_INVALID, "too many head rows per image");
+  // --- arena: first-fit over live intervals ---
+  struct Live { size_t off, bytes; int last; };
+  std::vector<Live> live;
+  std::vector<int> order_idx;
+  for (int b = 0; b < (int)e->bufs.size(); ++b) if (e->bufs[b].last >= 0) order_idx.push_back(b);
+  std::sort(order_idx.begin(), order_idx.end(), [&](int a, int b) { return e->bufs[a].first < e->bufs[b].first; });
+  size_t top = 0;
+  for (int b : order_idx) {
+    Buf& B = e->bufs[b];
+    const size_t need = (B.bytes + 1023) & ~(size_t)1023;
+    std::vector<Live> still;
+    for (const Live& l : live) if (l.last >= B.first) still.push_back(l);
+    live.swap(still);
+    std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
+    size_t off = 0;
+    for (const Live& l : live) {
+      if (off + need <= l.off) break;
+      off = std::max(off, l.off + l.bytes);
+    }
+    B.off = off;
+    live.push_back(Live{off, need, B.keep ? INT_MAX : B.last});
+    top = std::max(top, off + need);
+  }
+  e->arena_bytes = top + 1024;
+  return YB_OK;
+}
+
+static int build_tensor_maps(yb_engine* e) {
+  for (Op& op : e->ops) {
+    if (op.kind != OP_CONV || op.path != PATH_TC) continue;
+    const void* in_ptr = view_ptr(e, op.in);
+    if (op.ksize == 1 && op.stride == 1) {
+      YB_TRY(make_tiled_map(&op.tmA, in_ptr, (long long)e->max_batch * op.in.h * op.in.w, op.cin, op.in.ld, 128, op.bk));
+    } else {
+      YB_TRY(make_im2col_map(&op.tmA, in_ptr, e->max_batch, op.in.h, op.in.w, op.cin, op.in.ld, op.ksize, op.stride, op.pad, op.bk));
+    }
+    const int K = op.ksize * op.ksize * op.cin;
+    YB_TRY(make_tiled_map(&op.tmB, op.d_wt, op.cout_pad, K, K, op.bn_tile, op.bk));
+  }
+  return YB_OK;
+}
+
+static int ensure_scratch(yb_engine* e, size_t floats) {
+  if (floats <= e->scratch_floats) return YB_OK;
+  if (e->scratch_f32) cudaFree(e->scratch_f32);
+  e->scratch_f32 = nullptr; e->scratch_floats = 0;
+  YB_CUDA(cudaMalloc(&e->scratch_f32, floats * 4));
+  e->scratch_floats = floats;
+  return YB_OK;
+}
+
+static void engine_scales(const yb_engine* e, ScaleDesc* sc) {
+  for (size_t i = 0; i < e->heads.size(); ++i) {
+    const Head& hd = e->heads[i];
+    ScaleDesc& s = sc[i];
+    s.base = reinterpret_cast<const float*>(view_ptr(e, hd.view));
+    s.cell_stride = hd.view.ld;
+    s.img_stride = (long long)hd.h * hd.w * hd.view.ld;
+    s.h = hd.h; s.w = hd.w; s.na = hd.na; s.row_begin = hd.row_begin;
+    memcpy(s.anchors, hd.anchors, sizeof(float) * 2 * hd.na);
+  }
+}
+
+static int set_device(int device) {
+  int count = 0;
+  cudaError_t er = cudaGetDeviceCount(&count);
+  if (er != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(YB_ERR_CUDA, "no usable CUDA device (%s); libyolo_b200 has no CPU fallback", er == cudaSuccess ? "device count is 0" : cudaGetErrorString(er));
+  }
+  if (device < 0 || device >= count) return fail(YB_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+  YB_CUDA(cudaSetDevice(device));
+  return YB_OK;
+}
+
+}  // namespace yb
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int yb_abi_version(void) { return YB_ABI_VERSION; }
+const char* yb_last_error(void) { return g_err; }
+
+int yb_device_count(int* count) {
+  if (!count) return fail(YB_ERR_INVALID, "count is NULL");
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+  *count = c;
+  return YB_OK;
+}
+
+int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int in_c, int max_batch, int device,
+                     int decode_mode, int num_classes, yb_engine** out) {
+  if (!plan || !out || n_layers < 2 || in_h <= 0 || in_w <= 0 || in_c <= 0 || max_batch <= 0 || num_classes <= 0)
+    return fail(YB_ERR_INVALID, "yb_engine_create: bad argument");
+  YB_TRY(set_device(device));
+  YB_TRY(load_driver_fns());
+  yb_engine* e = new yb_engine();
+  e->device = device; e->H = in_h; e->W = in_w; e->C = in_c; e->max_batch = max_batch;
+  e->decode_mode = decode_mode; e->num_classes = num_classes;
+  e->plan.assign(plan, plan + n_layers);
+  const char* ka = getenv("YB_KEEP_ALL");
+  e->keep_all = ka && atoi(ka) != 0;
+  const char* bm = getenv("YB_BN_MAX");
+  if (bm && (atoi(bm) == 32 || atoi(bm) == 64 || atoi(bm) == 128 || atoi(bm) == 256)) e->bn_max = atoi(bm);
+  int r = compile_plan(e);
+  if (r == YB_OK) {
+    auto go = [&]() -> int {
+      YB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+      YB_CUDA(cudaMalloc(&e->arena, e->arena_bytes));
+      YB_CUDA(cudaMemset(e->arena, 0, e->arena_bytes));
+      YB_CUDA(cudaMalloc(&e->input_dev, (size_t)max_batch * in_h * in_w * in_c * 4));
+      float lut[256];
+      for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);   // image / 255. (net/base.py:153) then the fp32 feed cast
+      YB_CUDA(cudaMalloc(&e->d_u8_lut, sizeof(lut)));
+      YB_CUDA(cudaMemcpy(e->d_u8_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+      YB_TRY(e->post.alloc(max_batch, e->rows, e->box_len, decode_mode == YB_DECODE_V2));
+      e->post.n_scales = (int)e->heads.size();
+      return YB_OK;
+    };
+    r = go();
+  }
+  if (r != YB_OK) { yb_engine_destroy(e); return r; }
+  *out = e;
+  return YB_OK;
+}
+
+void yb_engine_destroy(yb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (Op& op : e->ops) { cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift); }
+  cudaFree(e->arena); cudaFree(e->input_dev); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
+  e->post.release();
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* consumed) {
+  if (!e || !stream) return fail(YB_ERR_INVALID, "yb_engine_load_weights: bad argument");
+  YB_TRY(set_device(e->device));
+  size_t need = 0;
+  for (const Op& op : e->ops)
+    if (op.kind == OP_CONV) need += (size_t)(e->plan[op.layer].batch_norm ? 4 : 1) * op.cout + (size_t)op.cout * op.cin * op.ksize * op.ksize;
+  if (n < need) {
+    if (consumed) *consumed = 0;
+    return fail(YB_ERR_SHORT_WEIGHTS, "weight stream has %zu floats, the plan needs %zu", n, need);
+  }
+  size_t read = 0;
+  std::vector<uint16_t> packed;
+  std::vector<float> packed32, scale, shift;
+  for (Op& op : e->ops) {
+    if (op.kind != OP_CONV) continue;
+    const int co = op.cout, ci = op.cin, k = op.ksize, K = k * k * ci;
+    const bool bn = e->plan[op.layer].batch_norm != 0;
+    scale.assign(op.cout_pad, 0.0f); shift.assign(op.cout_pad, 0.0f);
+    if (bn) {   // stream order: beta, gamma, moving_mean, moving_variance (net/layers.py:53-63)
+      const float *beta = stream + read, *gamma = beta + co, *mean = gamma + co, *var = mean + co;
+      for (int o = 0; o < co; ++o) {
+        const double inv = (double)gamma[o] / std::sqrt((double)var[o] + 1e-5);
+        scale[o] = (float)inv;
+        shift[o] = (float)((double)beta[o] - (double)mean[o] * inv);
+      }
+      read += 4 * (size_t)co;
+    } else {
+      for (int o = 0; o < co; ++o) { scale[o] = 1.0f; shift[o] = stream[read + o]; }
+      read += co;
+    }
+    const float* kern = stream + read;   // [O][I][kh][kw] (net/base.py:36-40)
+    read += (size_t)co * K;
+    cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift);
+    op.d_wt = nullptr; op.d_wt32 = nullptr; op.d_scale = nullptr; op.d_shift = nullptr;
+    if (op.path == PATH_DIRECT) {
+      packed32.assign((size_t)K * co, 0.0f);
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+          for (int t = 0; t < k * k; ++t) packed32[(size_t)(t * ci + i) * co + o] = kern[((size_t)o * ci + i) * k * k + t];
+      YB_CUDA(cudaMalloc(&op.d_wt32, packed32.size() * 4));
+      YB_CUDA(cudaMemcpy(op.d_wt32, packed32.data(), packed32.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      packed.assign((size_t)op.cout_pad * K, 0);
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+          for (int t = 0; t < k * k; ++t) packed[(size_t)o * K + t * ci + i] = f32_to_bf16_rne(kern[((size_t)o * ci + i) * k * k + t]);
+      YB_CUDA(cudaMalloc(&op.d_wt, packed.size() * 2));
+      YB_CUDA(cudaMemcpy(op.d_wt, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    }
+    YB_CUDA(cudaMalloc(&op.d_scale, (size_t)op.cout_pad * 4));
+    YB_CUDA(cudaMalloc(&op.d_shift, (size_t)op.cout_pad * 4));
+    YB_CUDA(cudaMemcpy(op.d_scale, scale.data(), (size_t)op.cout_pad * 4, cudaMemcpyHostToDevice));
+    YB_CUDA(cudaMemcpy(op.d_shift, shift.data(), (size_t)op.cout_pad * 4, cudaMemcpyHostToDevice));
+  }
+  if (consumed) *consumed = read;
+  YB_TRY(build_tensor_maps(e));
+  e->weights_loaded = true;
+  return YB_OK;
+}
+
+static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, int n, cudaEvent_t* evs, int* n_ev) {
+  if (!e || !images) return fail(YB_ERR_INVALID, "yb_engine_forward: bad argument");
+  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
+  if (dtype != YB_F32 && dtype != YB_U8) return fail(YB_ERR_INVALID, "unknown image dtype %d", dtype);
+  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_forward before yb_engine_load_weights");
+  YB_TRY(set_device(e->device));
+  const size_t bytes = (size_t)n * e->H * e->W * e->C * (dtype == YB_F32 ? 4 : 1);
+  if (mem == YB_MEM_HOST) {
+    YB_CUDA(cudaMemcpyAsync(e->input_dev, images, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->cur_input = e->input_dev;
+  } else {
+    e->cur_input = images;
+  }
+  e->cur_input_dtype = dtype;
+  e->fwd_launches = 0;
+  int k = 0;
+  for (Op& op : e->ops) {
+    if (evs) YB_CUDA(cudaEventRecord(evs[k], e->stream));
+    YB_TRY(run_op(e, op, n));
+    ++e->fwd_launches;
+    ++k;
+  }
+  if (evs) { YB_CUDA(cudaEventRecord(evs[k], e->stream)); *n_ev = k + 1; }
+  e->last_n = n;
+  e->detected = false;
+  return YB_OK;
+}
+
+int yb_engine_forward(yb_engine* e, const void* images, int dtype, int mem, int n) {
+  return forward_impl(e, images, dtype, mem, n, nullptr, nullptr);
+}
+
+int yb_engine_output_shape(yb_engine* e, int* rows, int* cols) {
+  if (!e || !rows || !cols) return fail(YB_ERR_INVALID, "yb_engine_output_shape: bad argument");
+  if (e->decode_mode == YB_DECODE_V2) { *rows = e->heads[0].h * e->heads[0].w; *cols = e->heads[0].na * e->box_len; }
+  else { *rows = e->rows; *cols = e->box_len; }
+  return YB_OK;
+}
+
+int yb_engine_read_output(yb_engine* e, float* host_out, size_t capacity) {
+  if (!e || !host_out) return fail(YB_ERR_INVALID, "yb_engine_read_output: bad argument");
+  if (e->last_n <= 0) return fail(YB_ERR_STATE, "yb_engine_read_output before yb_engine_forward");
+  YB_TRY(set_device(e->device));
+  const size_t total = (size_t)e->last_n * e->rows * e->box_len;
+  if (capacity < total) return fail(YB_ERR_CAPACITY, "output needs %zu floats, buffer holds %zu", total, capacity);
+  YB_TRY(ensure_scratch(e, total));
+  // [n, R, 5+C]; for v2 this is bit-for-bit the reference's [n, h, w, A*(5+C)] (rows = (cy*w+cx)*A + a)
+  for (const Head& hd : e->heads) {
+    const long long cnt = (long long)e->last_n * hd.h * hd.w * hd.na * e->box_len;
+    gather_head_kernel<<<ceil_div(cnt, 256), 256, 0, e->stream>>>(reinterpret_cast<const float*>(view_ptr(e, hd.view)), hd.view.ld,
+                                                                 hd.h * hd.w, hd.na, e->box_len, hd.row_begin, e->rows, e->scratch_f32, cnt);
+    YB_CUDA(cudaGetLastError());
+  }
+  YB_CUDA(cudaMemcpyAsync(host_out, e->scratch_f32, total * 4, cudaMemcpyDeviceToHost, e->stream));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  return YB_OK;
+}
+
+int yb_engine_read_layer(yb_engine* e, int layer, float* host_out, size_t capacity, int shape_hwc[3]) {
+  if (!e || !host_out || !shape_hwc) return fail(YB_ERR_INVALID, "yb_engine_read_layer: bad argument");
+  if (layer < 0 || layer >= (int)e->plan.size()) return fail(YB_ERR_INVALID, "layer %d out of range", layer);
+  if (e->last_n <= 0) return fail(YB_ERR_STATE, "yb_engine_read_layer before yb_engine_forward");
+  YB_TRY(set_device(e->device));
+  const View& v = e->view[layer];
+  if (v.buf == -1) return fail(YB_ERR_INVALID, "layer %d is fused into its consumer and has no tensor of its own", layer);
+  if (v.buf >= 0 && !e->keep_all && !e->bufs[v.buf].keep)
+    return fail(YB_ERR_STATE, "layer %d's buffer is recycled by the arena; create the engine with YB_KEEP_ALL=1 to read intermediates", layer);
+  const size_t total = (size_t)e->last_n * v.h * v.w * v.c;
+  if (capacity < total) return fail(YB_ERR_CAPACITY, "layer needs %zu floats, buffer holds %zu", total, capacity);
+  shape_hwc[0] = v.h; shape_hwc[1] = v.w; shape_hwc[2] = v.c;
+  YB_TRY(ensure_scratch(e, total));
+  if (v.buf == -2 && e->cur_input_dtype == YB_U8) return fail(YB_ERR_INVALID, "reading back a uint8 input is not supported");
+  read_view_kernel<<<ceil_div((long long)total, 256), 256, 0, e->stream>>>(view_ptr(e, v), v.ld, v.c, v.f32 ? 1 : 0, e->scratch_f32, (long long)total);
+  YB_CUDA(cudaGetLastError());
+  YB_CUDA(cudaMemcpyAsync(host_out, e->scratch_f32, total * 4, cudaMemcpyDeviceToHost, e->stream));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  return YB_OK;
+}
+
+int yb_engine_detect_async(yb_engine* e, float threshold, float iou_threshold, int nms_mode) {
+  if (!e) return fail(YB_ERR_INVALID, "yb_engine_detect: engine is NULL");
+  if (e->last_n <= 0) return fail(YB_ERR_STATE, "yb_engine_detect before yb_engine_forward");
+  if (nms_mode != YB_NMS_REFERENCE && nms_mode != YB_NMS_PER_CLASS) return fail(YB_ERR_INVALID, "unknown nms mode %d", nms_mode);
+  YB_TRY(set_device(e->device));
+  ScaleDesc sc[POST_MAX_SCALES];
+  engine_scales(e, sc);
+  YB_TRY(e->post.decode(e->stream, sc, e->last_n, threshold));
+  // the reference compares the float64 IoU with the Python float threshold (net/base.py:203)
+  YB_TRY(e->post.nms(e->stream, e->last_n, (double)iou_threshold, nms_mode));
+  e->det_launches = 2;
+  e->detected = true;
+  return YB_OK;
+}
+
+static int copy_dets(PostCtx& post, cudaStream_t st, int n, yb_det* out, int* counts, int max_per_image, int* det_launches) {
+  if (max_per_image <= 0) return fail(YB_ERR_INVALID, "max_per_image must be positive");
+  if ((size_t)n * max_per_image > post.dets_cap) max_per_image = (int)(post.dets_cap / n);
+  YB_TRY(post.gather(st, n, max_per_image));
+  if (det_launches) ++*det_launches;
+  static_assert(sizeof(yb_det) == sizeof(DetOut), "yb_det layout");
+  YB_CUDA(cudaMemcpyAsync(counts, post.n_keep, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaMemcpyAsync(out, post.dets, (size_t)n * max_per_image * sizeof(DetOut), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  return YB_OK;
+}
+
+int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode, yb_det* out, int* counts, int max_per_image) {
+  if (!out || !counts) return fail(YB_ERR_INVALID, "yb_engine_detect: output buffers are NULL");
+  YB_TRY(yb_engine_detect_async(e, threshold, iou_threshold, nms_mode));
+  if (max_per_image > e->rows) max_per_image = e->rows;
+  return copy_dets(e->post, e->stream, e->last_n, out, counts, max_per_image, &e->det_launches);
+}
+
+int yb_engine_sync(yb_engine* e) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  return YB_OK;
+}
+
+int yb_engine_profile(yb_engine* e, const void* images, int dtype, int mem, int n, int* layer_idx, float* ms, int cap, int* n_ops) {
+  if (!e || !layer_idx || !ms || !n_ops) return fail(YB_ERR_INVALID, "yb_engine_profile: bad argument");
+  YB_TRY(set_device(e->device));
+  const int nops = (int)e->ops.size();
+  std::vector<cudaEvent_t> evs(nops + 1);
+  for (auto& ev : evs) YB_CUDA(cudaEventCreate(&ev));
+  int n_ev = 0;
+  int r = forward_impl(e, images, dtype, mem, n, evs.data(), &n_ev);
+  if (r == YB_OK) {
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) r = fail(YB_ERR_CUDA, "profile sync failed: %s", cudaGetErrorString(ce));
+  }
+  if (r == YB_OK) {
+    *n_ops = nops;
+    for (int i = 0; i < nops && i < cap; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
+      ms[i] = t;
+      layer_idx[i] = e->ops[i].layer;
+    }
+  }
+  for (auto& ev : evs) cudaEventDestroy(ev);
+  return r;
+}
+
+int yb_engine_set_conv_impl(yb_engine* e, int impl) {
+  if (!e || (impl != 0 && impl != 1)) return fail(YB_ERR_INVALID, "yb_engine_set_conv_impl: bad argument");
+  e->conv_impl = impl;
+  return YB_OK;
+}
+
+int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  if (forward_launches) *forward_launches = e->fwd_launches;
+  if (detect_launches) *detect_launches = e->det_launches;
+  return YB_OK;
+}
+
+// ---- stand-alone post-processing ----
+struct yb_post {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  PostCtx ctx;
+  float* staging = nullptr;   // device copy of host head tensors
+  size_t staging_floats = 0;
+  int num_classes = 0, decode_mode = 0;
+  float decode_ms = 0.f, nms_ms = 0.f;
+  bool timed = false;
+};
+
+int yb_post_create(const yb_scale* scales, int n_scales, int num_classes, int decode_mode, int max_batch, int device, yb_post** out) {
+  if (!scales || !out || n_scales < 1 || n_scales > POST_MAX_SCALES || num_classes <= 0 || max_batch <= 0)
+    return fail(YB_ERR_INVALID, "yb_post_create: bad argument");
+  YB_TRY(set_device(device));
+  yb_post* p = new yb_post();
+  p->device = device; p->num_classes = num_classes; p->decode_mode = decode_mode;
+  int rows = 0;
+  for (int i = 0; i < n_scales; ++i) {
+    if (scales[i].n_anchors < 1 || scales[i].n_anchors > YB_MAX_ANCHORS || scales[i].h <= 0 || scales[i].w <= 0) {
+      delete p;
+      return fail(YB_ERR_INVALID, "yb_post_create: bad scale %d", i);
+    }
+    ScaleDesc& s = p->ctx.scales[i];
+    memset(&s, 0, sizeof(s));
+    s.h = scales[i].h; s.w = scales[i].w; s.na = scales[i].n_anchors; s.row_begin = rows;
+    memcpy(s.anchors, scales[i].anchors, sizeof(float) * 2 * s.na);
+    rows += s.h * s.w * s.na;
+  }
+  auto go = [&]() -> int {
+    YB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    YB_TRY(p->ctx.alloc(max_batch, rows, 5 + num_classes, decode_mode == YB_DECODE_V2));
+    p->ctx.n_scales = n_scales;
+    return YB_OK;
+  };
+  int r = go();
+  if (r != YB_OK) { yb_post_destroy(p); return r; }
+  *out = p;
+  return YB_OK;
+}
+
+void yb_post_destroy(yb_post* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  p->ctx.release();
+  cudaFree(p->staging);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+static int post_stage_and_decode(yb_post* p, const float* head, int mem, int n, float threshold) {
+  if (!p || !head) return fail(YB_ERR_INVALID, "yb_post: bad argument");
+  if (n <= 0 || n > p->ctx.max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, p->ctx.max_batch);
+  YB_TRY(set_device(p->device));
+  const size_t floats = (size_t)n * p->ctx.rows * p->ctx.box_len;
+  const float* dev = head;
+  if (mem == YB_MEM_HOST) {
+    if (floats > p->staging_floats) {
+      cudaFree(p->staging); p->staging = nullptr; p->staging_floats = 0;
+      YB_CUDA(cudaMalloc(&p->staging, floats * 4));
+      p->staging_floats = floats;
+    }
+    YB_CUDA(cudaMemcpyAsync(p->staging, head, floats * 4, cudaMemcpyHostToDevice, p->stream));
+    dev = p->staging;
+  }
+  ScaleDesc sc[POST_MAX_SCALES];
+  for (int i = 0; i < p->ctx.n_scales; ++i) {
+    sc[i] = p->ctx.scales[i];
+    sc[i].base = dev + (long long)sc[i].row_begin * p->ctx.box_len;
+    sc[i].img_stride = (long long)p->ctx.rows * p->ctx.box_len;
+    sc[i].cell_stride = sc[i].na * p->ctx.box_len;
+  }
+  YB_CUDA(cudaEventRecord(p->ctx.ev[0], p->stream));
+  YB_TRY(p->ctx.decode(p->stream, sc, n, threshold));
+  YB_CUDA(cudaEventRecord(p->ctx.ev[1], p->stream));
+  return YB_OK;
+}
+
+int yb_post_run(yb_post* p, const float* head, int mem, int n, float threshold, float iou_threshold, int nms_mode,
+                yb_det* out, int* counts, int max_per_image, int* cand_counts) {
+  if (nms_mode != YB_NMS_REFERENCE && nms_mode != YB_NMS_PER_CLASS) return fail(YB_ERR_INVALID, "unknown nms mode %d", nms_mode);
+  YB_TRY(post_stage_and_decode(p, head, mem, n, threshold));
+  YB_TRY(p->ctx.nms(p->stream, n, (double)iou_threshold, nms_mode));
+  YB_CUDA(cudaEventRecord(p->ctx.ev[2], p->stream));
+  p->timed = true;
+  if (out && counts) {
+    if (max_per_image > p->ctx.rows) max_per_image = p->ctx.rows;
+    YB_TRY(copy_dets(p->ctx, p->stream, n, out, counts, max_per_image, nullptr));
+  }
+  if (cand_counts) {
+    YB_CUDA(cudaMemcpyAsync(cand_counts, p->ctx.n_cand, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+    YB_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  return YB_OK;
+}
+
+// identity "NMS": order = every candidate row (ascending), used to export the raw decode
+__global__ void list_candidates_kernel(int rows, const float* prob, int* order, int* n_keep) {
+  __shared__ int s_cnt;
+  const int img = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int r = 0; r < rows; ++r)
+      { const float pr = prob[(long long)img * rows + r]; if (pr == pr) order[(long long)img * rows + c++] = r; }
+    s_cnt = c;
+    n_keep[img] = c;
+  }
+}
+
+int yb_post_decode(yb_post* p, const float* head, int mem, int n, float threshold, yb_det* out, int* counts, int max_per_image) {
+  if (!out || !counts) return fail(YB_ERR_INVALID, "yb_post_decode: output buffers are NULL");
+  YB_TRY(post_stage_and_decode(p, head, mem, n, threshold));
+  list_candidates_kernel<<<n, 32, 0, p->stream>>>(p->ctx.rows, p->ctx.prob, p->ctx.order, p->ctx.n_keep);
+  YB_CUDA(cudaGetLastError());
+  if (max_per_image > p->ctx.rows) max_per_image = p->ctx.rows;
+  return copy_dets(p->ctx, p->stream, n, out, counts, max_per_image, nullptr);
+}
+
+int yb_post_sync(yb_post* p) {
+  if (!p) return fail(YB_ERR_INVALID, "post is NULL");
+  YB_TRY(set_device(p->device));
+  YB_CUDA(cudaStreamSynchronize(p->stream));
+  return YB_OK;
+}
+
+int yb_post_last_ms(yb_post* p, float* decode_ms, float* nms_ms) {
+  if (!p || !p->timed) return fail(YB_ERR_STATE, "yb_post_last_ms before yb_post_run");
+  YB_TRY(set_device(p->device));
+  YB_CUDA(cudaEventSynchronize(p->ctx.ev[2]));
+  float a = 0.f, b = 0.f;
+  YB_CUDA(cudaEventElapsedTime(&a, p->ctx.ev[0], p->ctx.ev[1]));
+  YB_CUDA(cudaEventElapsedTime(&b, p->ctx.ev[1], p->ctx.ev[2]));
+  if (decode_ms) *decode_ms = a;
+  if (nms_ms) *nms_ms = b;
+  return YB_OK;
+}
+
+int yb_nms(const void* x, const void* y, const void* w, const void* h, const float* prob, const int32_t* class_idx, int k,
+           int f64, double iou_threshold, int nms_mode, int device, int32_t* keep, int* n_keep) {
+  if (!keep || !n_keep || k < 0) return fail(YB_ERR_INVALID, "yb_nms: bad argument");
+  if (nms_mode != YB_NMS_REFERENCE && nms_mode != YB_NMS_PER_CLASS) return fail(YB_ERR_INVALID, "unknown nms mode %d", nms_mode);
+  if (nms_mode == YB_NMS_PER_CLASS && !class_idx) return fail(YB_ERR_INVALID, "per-class NMS needs class_idx");
+  if (k == 0) { *n_keep = 0; return YB_OK; }          // net/base.py:196-197
+  if (!x || !y || !w || !h || !prob) return fail(YB_ERR_INVALID, "yb_nms: NULL input array");
+  YB_TRY(set_device(device));
+  PostCtx ctx;
+  int r = ctx.alloc(1, k, 5, 0);
+  cudaStream_t st = nullptr;
+  void *dx = nullptr, *dy = nullptr, *dw = nullptr, *dh = nullptr;
+  auto go = [&]() -> int {
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t es = f64 ? 8 : 4;
+    YB_CUDA(cudaMalloc(&dx, k * es)); YB_CUDA(cudaMalloc(&dy, k * es)); YB_CUDA(cudaMalloc(&dw, k * es)); YB_CUDA(cudaMalloc(&dh, k * es));
+    YB_CUDA(cudaMemcpyAsync(dx, x, k * es, cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(dy, y, k * es, cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(dw, w, k * es, cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(dh, h, k * es, cudaMemcpyHostToDevice, st));
+    // a NaN score is the engine's "not a candidate" marker, so it cannot be a score here
+    for (int i = 0; i < k; ++i)
+      if (prob[i] != prob[i]) return fail(YB_ERR_INVALID, "yb_nms: box %d has a NaN score", i);
+    YB_CUDA(cudaMemcpyAsync(ctx.prob, prob, (size_t)k * 4, cudaMemcpyHostToDevice, st));
+    if (class_idx) YB_CUDA(cudaMemcpyAsync(ctx.cls, class_idx, (size_t)k * 4, cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemsetAsync(ctx.flags, 0, (size_t)k, st));
+    NmsArgs a = ctx.nms_args(f64 ? iou_threshold : (double)(float)iou_threshold, nms_mode == YB_NMS_PER_CLASS);
+    a.x = dx; a.y = dy; a.w = dw; a.h = dh;
+    a.cls = class_idx ? ctx.cls : nullptr;
+    if (f64) YB_TRY((ctx.nms_launch<double, true, true>(st, 1, a)));
+    else YB_TRY((ctx.nms_launch<float, false, false>(st, 1, a)));
+    YB_CUDA(cudaMemcpyAsync(n_keep, ctx.n_keep, 4, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    YB_CUDA(cudaMemcpy(keep, ctx.order, (size_t)(*n_keep) * 4, cudaMemcpyDeviceToHost));
+    return YB_OK;
+  };
+  if (r == YB_OK) r = go();
+  cudaFree(dx); cudaFree(dy); cudaFree(dw); cudaFree(dh);
+  if (st) cudaStreamDestroy(st);
+  ctx.release();
+  return r;
+}
+
+}  // extern "C"

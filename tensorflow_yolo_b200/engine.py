@@ -1,0 +1,226 @@
+"""Python handles over the C ABI: Engine (conv stack + detect), PostProcessor (decode+NMS on head
+tensors) and nms() (the reference's non_maximum_suppression on caller boxes).  No arithmetic here."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import plan as _plan
+from ._lib import DET_DTYPE, YB_DECODE_V2, YB_DECODE_V3, YB_NMS_PER_CLASS, YB_NMS_REFERENCE  # noqa: F401
+
+
+def _buffer(arr, np_dtypes):
+    """(pointer, mem, dtype code, keepalive) for a numpy array or a torch tensor (host or CUDA)."""
+    if isinstance(arr, np.ndarray):
+        if arr.dtype not in np_dtypes:
+            raise TypeError("expected dtype in {}, got {}".format(np_dtypes, arr.dtype))
+        a = np.ascontiguousarray(arr)
+        return a.ctypes.data, _lib.YB_MEM_HOST, a.dtype, a
+    if hasattr(arr, "data_ptr") and hasattr(arr, "is_cuda"):      # torch.Tensor without importing torch
+        if not arr.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        dt = np.dtype(str(arr.dtype).replace("torch.", ""))
+        if dt not in np_dtypes:
+            raise TypeError("expected dtype in {}, got {}".format(np_dtypes, dt))
+        return arr.data_ptr(), (_lib.YB_MEM_DEVICE if arr.is_cuda else _lib.YB_MEM_HOST), dt, arr
+    raise TypeError("expected a numpy array or a torch tensor")
+
+
+class Engine(object):
+    """One compiled network on one GPU (yb_engine)."""
+
+    def __init__(self, plan, input_shape, num_classes, decode_mode, max_batch=1, device=0):
+        self._h = None
+        self.plan = list(plan)
+        self.input_shape = tuple(int(s) for s in input_shape)
+        self.num_classes, self.decode_mode, self.max_batch, self.device = num_classes, decode_mode, max_batch, device
+        arr = _plan.to_c_array(self.plan)
+        handle = ctypes.c_void_p()
+        h, w, c = self.input_shape
+        _lib.check(_lib.lib().yb_engine_create(arr, len(self.plan), h, w, c, max_batch, device, decode_mode,
+                                               num_classes, ctypes.byref(handle)))
+        self._h = handle
+        rows, cols = ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().yb_engine_output_shape(self._h, ctypes.byref(rows), ctypes.byref(cols)))
+        self.out_rows, self.out_cols = rows.value, cols.value
+        self.last_n = 0
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().yb_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_weights(self, stream):
+        """stream: float32 darknet payload (header stripped).  Returns the number of floats consumed."""
+        stream = np.ascontiguousarray(stream, dtype=np.float32)
+        consumed = ctypes.c_size_t(0)
+        _lib.check(_lib.lib().yb_engine_load_weights(self._h, stream.ctypes.data, stream.size, ctypes.byref(consumed)))
+        return consumed.value
+
+    def forward(self, images):
+        """images: [n,H,W,C] float32 in [0,1] or uint8; numpy (host) or torch (host/CUDA).  Asynchronous."""
+        if isinstance(images, np.ndarray) and images.dtype == np.float64:
+            images = images.astype(np.float32)       # the reference feeds float64 into a float32 placeholder
+        ptr, mem, dt, keep = _buffer(images, (np.dtype(np.float32), np.dtype(np.uint8)))
+        shape = tuple(images.shape)
+        if len(shape) != 4 or shape[1:] != self.input_shape:
+            raise ValueError("expected images of shape [n,{},{},{}], got {}".format(*(self.input_shape + (shape,))))
+        self._keep = keep
+        _lib.check(_lib.lib().yb_engine_forward(self._h, ptr, _lib.YB_F32 if dt == np.float32 else _lib.YB_U8, mem, shape[0]))
+        self.last_n = shape[0]
+
+    def read_output(self):
+        """The reference's net[-1].out for the last forward, as float32 numpy."""
+        n = self.last_n
+        out = np.empty((n, self.out_rows, self.out_cols), dtype=np.float32)
+        _lib.check(_lib.lib().yb_engine_read_output(self._h, out.ctypes.data, out.size))
+        return out
+
+    def read_layer(self, index):
+        """NHWC float32 value of plan entry `index` (needs YB_KEEP_ALL=1 for recycled intermediates)."""
+        spec = self.plan[index]
+        n = self.last_n
+        cap = n * int(np.prod(spec.shape)) if spec.kind not in (_plan.KIND_YOLO, _plan.KIND_DETECTION) else 0
+        if cap == 0:
+            raise ValueError("layer {} has no NHWC tensor".format(index))
+        out = np.empty(cap, dtype=np.float32)
+        hwc = (ctypes.c_int * 3)()
+        _lib.check(_lib.lib().yb_engine_read_layer(self._h, index, out.ctypes.data, out.size, ctypes.byref(hwc)))
+        return out.reshape(n, hwc[0], hwc[1], hwc[2])
+
+    def detect(self, threshold, iou_threshold, nms_mode=YB_NMS_REFERENCE, max_per_image=None):
+        """decode + NMS of the last forward.  Returns a list (per image) of structured arrays (DET_DTYPE)
+        in kept order."""
+        n = self.last_n
+        cap = int(max_per_image or 256)
+        while True:
+            dets = np.zeros((n, cap), dtype=DET_DTYPE)
+            counts = np.zeros(n, dtype=np.int32)
+            _lib.check(_lib.lib().yb_engine_detect(self._h, threshold, iou_threshold, nms_mode,
+                                                   dets.ctypes.data, counts.ctypes.data, cap))
+            if max_per_image is not None or counts.max(initial=0) <= cap:
+                break
+            cap = int(counts.max())          # rare: more detections than the first guess; fetch again
+        return [dets[i, :min(int(counts[i]), cap)] for i in range(n)]
+
+    def detect_async(self, threshold, iou_threshold, nms_mode=YB_NMS_REFERENCE):
+        _lib.check(_lib.lib().yb_engine_detect_async(self._h, threshold, iou_threshold, nms_mode))
+
+    def sync(self):
+        _lib.check(_lib.lib().yb_engine_sync(self._h))
+
+    def set_conv_impl(self, impl):
+        _lib.check(_lib.lib().yb_engine_set_conv_impl(self._h, impl))
+
+    def launch_count(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().yb_engine_launch_count(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def profile(self, images):
+        """[(plan layer index, milliseconds)] per launched op for one forward (CUDA events)."""
+        ptr, mem, dt, keep = _buffer(images, (np.dtype(np.float32), np.dtype(np.uint8)))
+        cap = 4 * len(self.plan)
+        idx = np.zeros(cap, dtype=np.int32)
+        ms = np.zeros(cap, dtype=np.float32)
+        n_ops = ctypes.c_int()
+        _lib.check(_lib.lib().yb_engine_profile(self._h, ptr, _lib.YB_F32 if dt == np.float32 else _lib.YB_U8, mem,
+                                                images.shape[0], idx.ctypes.data, ms.ctypes.data, cap, ctypes.byref(n_ops)))
+        self.last_n = images.shape[0]
+        return [(int(idx[i]), float(ms[i])) for i in range(min(n_ops.value, cap))]
+
+
+class PostProcessor(object):
+    """Stand-alone decode + NMS over head tensors in the reference's net[-1].out layout (yb_post)."""
+
+    def __init__(self, scales, num_classes, decode_mode, max_batch=1, device=0):
+        """scales: [(h, w, [(aw, ah), ...])] with anchors in grid units, in detection order."""
+        self._h = None
+        arr = (_lib.yb_scale * len(scales))()
+        self.rows = 0
+        for i, (h, w, anchors) in enumerate(scales):
+            arr[i].h, arr[i].w, arr[i].n_anchors = int(h), int(w), len(anchors)
+            for j, (aw, ah) in enumerate(anchors):
+                arr[i].anchors[2 * j], arr[i].anchors[2 * j + 1] = float(aw), float(ah)
+            self.rows += int(h) * int(w) * len(anchors)
+        self.box_len = 5 + num_classes
+        self.max_batch = max_batch
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().yb_post_create(arr, len(scales), num_classes, decode_mode, max_batch, device,
+                                             ctypes.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().yb_post_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _head(self, head):
+        ptr, mem, _, keep = _buffer(head, (np.dtype(np.float32),))
+        n = int(head.shape[0])
+        if int(np.prod(head.shape[1:])) != self.rows * self.box_len:
+            raise ValueError("head tensor has {} values per image, expected {}".format(
+                int(np.prod(head.shape[1:])), self.rows * self.box_len))
+        return ptr, mem, n, keep
+
+    def run(self, head, threshold, iou_threshold, nms_mode=YB_NMS_REFERENCE, max_per_image=None, fetch=True):
+        ptr, mem, n, keep = self._head(head)
+        if not fetch:
+            _lib.check(_lib.lib().yb_post_run(self._h, ptr, mem, n, threshold, iou_threshold, nms_mode, None, None, 0, None))
+            return None
+        cap = int(max_per_image or self.rows)
+        dets = np.zeros((n, cap), dtype=DET_DTYPE)
+        counts = np.zeros(n, dtype=np.int32)
+        cands = np.zeros(n, dtype=np.int32)
+        _lib.check(_lib.lib().yb_post_run(self._h, ptr, mem, n, threshold, iou_threshold, nms_mode,
+                                          dets.ctypes.data, counts.ctypes.data, cap, cands.ctypes.data))
+        self.last_candidates = cands
+        return [dets[i, :min(int(counts[i]), cap)] for i in range(n)]
+
+    def decode(self, head, threshold):
+        """All candidates (before NMS) per image, sorted by row."""
+        ptr, mem, n, keep = self._head(head)
+        cap = self.rows
+        dets = np.zeros((n, cap), dtype=DET_DTYPE)
+        counts = np.zeros(n, dtype=np.int32)
+        _lib.check(_lib.lib().yb_post_decode(self._h, ptr, mem, n, threshold, dets.ctypes.data, counts.ctypes.data, cap))
+        return [dets[i, :int(counts[i])] for i in range(n)]
+
+    def sync(self):
+        _lib.check(_lib.lib().yb_post_sync(self._h))
+
+    def last_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _lib.check(_lib.lib().yb_post_last_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+
+def nms(x, y, w, h, prob, iou_threshold, class_idx=None, nms_mode=YB_NMS_REFERENCE, device=0):
+    """Greedy NMS on the device with the reference's semantics (net/base.py:195-209).  If any coordinate
+    array is float64 the IoU is evaluated in float64 (as numpy would), otherwise in float32.
+    Returns kept indices in kept order."""
+    arrs = [np.asarray(a) for a in (x, y, w, h)]
+    f64 = any(a.dtype == np.float64 for a in arrs)
+    dt = np.float64 if f64 else np.float32
+    arrs = [np.ascontiguousarray(a, dtype=dt) for a in arrs]
+    prob = np.ascontiguousarray(prob, dtype=np.float32)
+    k = prob.size
+    cls = None if class_idx is None else np.ascontiguousarray(class_idx, dtype=np.int32)
+    keep = np.zeros(max(k, 1), dtype=np.int32)
+    n_keep = ctypes.c_int(0)
+    _lib.check(_lib.lib().yb_nms(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data,
+                                 prob.ctypes.data, None if cls is None else cls.ctypes.data, k, int(f64),
+                                 float(iou_threshold), nms_mode, device, keep.ctypes.data, ctypes.byref(n_keep)))
+    return keep[:n_keep.value].astype(np.int64)

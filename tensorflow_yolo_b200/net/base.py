@@ -1,0 +1,217 @@
+"""Host-side utilities with the reference's names (net/base.py), routed to the CUDA engine.
+
+What moved to the device: ``load_weights`` (net/base.py:26-46 -> yb_engine_load_weights),
+``non_maximum_suppression`` / ``iou_score`` (net/base.py:180-209 -> yb_nms), the forward pass behind
+``Session.run``.  What stays on the host, unchanged in behaviour: image listing, cv2 preprocessing,
+box drawing / saving (net/base.py:64-66,115-168,212-230) -- they sit outside the hot path.
+"""
+import os
+
+import numpy as np
+
+from .. import _lib
+from .. import engine as _engine
+from .. import plan as _plan
+
+COLORS = [(0, 0, 255), (0, 255, 0), (255, 0, 0), (0, 255, 255), (255, 255, 0), (255, 0, 255)]
+
+
+class BoundingBox(object):
+    """Result record, field-compatible with the reference's BoundingBox (net/base.py:257-272)."""
+
+    def __init__(self, x=0., y=0., w=0., h=0., cx=0, cy=0, class_idx=-1, prob=-1.):
+        self.x, self.y, self.w, self.h = x, y, w, h
+        self.cx, self.cy = cx, cy
+        self.class_idx = class_idx
+        self.prob = prob
+
+    def get_top_left(self, h=1., w=1.):
+        return (self.x - self.w / 2.) * w, (self.y - self.h / 2.) * h
+
+    def get_bottom_right(self, h=1., w=1.):
+        return (self.x + self.w / 2.) * w, (self.y + self.h / 2.) * h
+
+    def __repr__(self):
+        return "BoundingBox(x={:.4f}, y={:.4f}, w={:.4f}, h={:.4f}, class_idx={}, prob={:.4f})".format(
+            float(self.x), float(self.y), float(self.w), float(self.h), int(self.class_idx), float(self.prob))
+
+
+def boxes_from_dets(dets):
+    """Structured yb_det array -> list of BoundingBox with the dtypes the reference produces
+    (x, y, prob float32; w, h float64; class_idx int64)."""
+    return [BoundingBox(x=d["x"], y=d["y"], w=d["w"], h=d["h"], class_idx=np.int64(d["class_idx"]), prob=d["prob"])
+            for d in dets]
+
+
+class NetworkState(object):
+    """Per-network runtime attached to the layer list: the plan, the engine and its head geometry."""
+
+    def __init__(self, graph, version, num_classes, anchors_v2=None, input_shape=(416, 416, 3)):
+        self.graph = graph
+        self.version = version
+        self.num_classes = num_classes
+        self.anchors_v2 = anchors_v2
+        self.input_shape = tuple(input_shape)
+        self.engine = None
+        self.max_batch = 0
+        self.device = int(os.environ.get("YB_DEVICE", "0"))
+        self.pending_stream = None
+
+    def plan(self):
+        specs = list(self.graph.specs)
+        if self.version == "v2":
+            # the reference's v2 plan ends in the linear conv (net/v2.py:52-59); the engine needs the
+            # head geometry, carried by one trailing YOLO entry (anchors are already in grid units)
+            last = specs[-1]
+            h, w, c = last.shape
+            specs.append(_plan.LayerSpec(_plan.KIND_YOLO, (1, h * w * len(self.anchors_v2), 5 + self.num_classes),
+                                         src=[len(specs) - 1], anchors=self.anchors_v2))
+        return specs
+
+    def ensure_engine(self, batch):
+        if self.engine is not None and batch <= self.max_batch:
+            return self.engine
+        if self.engine is not None:
+            self.engine.close()
+        mode = _engine.YB_DECODE_V2 if self.version == "v2" else _engine.YB_DECODE_V3
+        self.max_batch = max(int(batch), int(os.environ.get("YB_MAX_BATCH", "1")))
+        self.engine = _engine.Engine(self.plan(), self.input_shape, self.num_classes, mode,
+                                     max_batch=self.max_batch, device=self.device)
+        if self.pending_stream is not None:
+            self.engine.load_weights(self.pending_stream)
+        return self.engine
+
+
+def state_of(layers):
+    st = getattr(layers[0], "_yb_state", None)
+    if st is None:
+        raise ValueError("this layer list was not built by tensorflow_yolo_b200.net.v2/v3")
+    return st
+
+
+class _AssignWeights(object):
+    """The 'op' returned by load_weights; executing it (Session.run) uploads the stream to the engine."""
+
+    def __init__(self, state, stream, read):
+        self.state, self.stream, self.read = state, stream, read
+
+    def run(self):
+        self.state.pending_stream = self.stream
+        if self.state.engine is not None:
+            self.state.engine.load_weights(self.stream)
+
+
+def load_weights(layers, weights):
+    """Same contract as the reference's base.load_weights(layers, weights): walks layer.variable_names in
+    order, checks the stream is long enough (the reference raises ValueError from np.reshape on a short
+    stream, net/base.py:38) and returns the list of assign ops to hand to Session.run."""
+    state = state_of(layers)
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    need = _plan.weight_count(state.graph.specs)
+    if len(weights) < need:
+        raise ValueError("cannot reshape array of size {} into the network's {} weight values".format(
+            len(weights), need))
+    print("Weights ready ({}/{} read)".format(need, len(weights)))
+    return [_AssignWeights(state, weights, need)]
+
+
+class Session(object):
+    """Minimal stand-in for tf.Session on the TEST path: run(ops) uploads weights,
+    run(net[-1].out, {net[0].out: x}) runs the conv stack on the GPU."""
+
+    def __init__(self, layers=None):
+        self.layers = layers
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def run(self, fetches, feed_dict=None):
+        if isinstance(fetches, (list, tuple)) and all(isinstance(f, _AssignWeights) for f in fetches):
+            for f in fetches:
+                f.run()
+            return None
+        if feed_dict is None or len(feed_dict) != 1:
+            raise ValueError("feed exactly the input placeholder")
+        (placeholder, x_batch), = feed_dict.items()
+        state = placeholder.graph._yb_state
+        if fetches.graph is not placeholder.graph:
+            raise ValueError("fetch and feed belong to different networks")
+        x = np.asarray(x_batch)
+        eng = state.ensure_engine(x.shape[0])
+        eng.forward(x)
+        out = eng.read_output()
+        if state.version == "v2":
+            h, w, _ = state.graph.specs[-1].shape
+            out = out.reshape(x.shape[0], h, w, -1)
+        return out
+
+
+def load_checkpoint_by_path(saver, sess, checkpoint_path):
+    """TF tensor-bundle checkpoints are not readable without TensorFlow yet; behave like
+    the reference's failure branch (net/base.py:55-61): report and return False so the caller falls back
+    to the darknet .weights file."""
+    print("Failed to load {}: TensorFlow checkpoints are not supported by tensorflow_yolo_b200".format(checkpoint_path))
+    return False
+
+
+def load_image_paths(path_to_img_dir):
+    return [os.path.join(os.path.abspath(path_to_img_dir), f) for f in os.listdir(path_to_img_dir)
+            if any(f.lower().endswith(ext) for ext in ["jpg", "bmp", "png", "gif"])]
+
+
+def preprocess_image(image_path, new_shape, objects=None, augment_prob=0.):
+    """cv2 read -> resize to new_shape[0:2] (passed as dsize, exactly like the reference, including its
+    (h, w)-as-(w, h) quirk on non-square inputs) -> BGR to RGB -> /255. (net/base.py:115-155)."""
+    import cv2
+    image = cv2.imread(image_path)
+    if image is None:
+        print("Failed to read {}".format(image_path))
+        return
+    net_image = cv2.resize(image, tuple(new_shape[0:2]))
+    net_image = net_image[:, :, ::-1]
+    return net_image / 255., None
+
+
+def generate_test_batch(img_paths, batch_size, input_shape):
+    total_batches = int(np.ceil(len(img_paths) / batch_size))
+    for b in range(total_batches):
+        images, paths = [], []
+        for i in range(min(batch_size, len(img_paths) - b * batch_size)):
+            image, _ = preprocess_image(img_paths[b * batch_size + i], input_shape, augment_prob=0.)
+            images.append(np.expand_dims(image, axis=0))
+            paths.append(img_paths[b * batch_size + i])
+        yield np.concatenate(images, axis=0), paths
+
+
+def non_maximum_suppression(boxes, iou_threshold):
+    """Greedy NMS on the GPU with the reference's ordering and tie-breaking (net/base.py:195-209)."""
+    if len(boxes) == 0:
+        return []
+    get = lambda name: np.asarray([getattr(b, name) for b in boxes])
+    keep = _engine.nms(get("x"), get("y"), get("w"), get("h"), get("prob").astype(np.float32), iou_threshold,
+                       device=int(os.environ.get("YB_DEVICE", "0")))
+    return [boxes[i] for i in keep]
+
+
+def draw_boxes(path_to_img, boxes, class_names):
+    import cv2
+    image = cv2.imread(path_to_img)
+    assert image is not None
+    h, w = image.shape[0:2]
+    for box in boxes:
+        tl = np.maximum(box.get_top_left(h, w), 0)
+        br = np.maximum(box.get_bottom_right(h, w), 0)
+        tl, br = (int(tl[0]), int(tl[1])), (int(br[0]), int(br[1]))
+        color = COLORS[int(box.class_idx) % len(COLORS)]
+        cv2.rectangle(image, tl, br, color, thickness=3)
+        cv2.putText(image, "{} {:.3f}".format(class_names[int(box.class_idx)], float(box.prob)), (tl[0], tl[1] - 10),
+                    cv2.FONT_HERSHEY_SIMPLEX, 0.5, color, thickness=1)
+    return image
+
+
+def save_image(image, out_path):
+    import cv2
+    cv2.imwrite(out_path, image)
