@@ -5,41 +5,76 @@ benches and parity tests run on random-init weights written in the reference's o
 (net/base.py:26-46 order; headers net/v3.py:101-104 and net/v2.py:68-77) -- the same file is read
 by the CUDA engine and by the CPU oracle.
 
-The initialisation is variance-preserving so that activations stay O(1) through all 75 (v3) /
-23 (v2) convs without any data-dependent calibration (a naive He init with random BN statistics
-overflows the 23-block residual trunk; TF's default glorot/identity-BN init collapses to 0):
+Initialisation (kernels first, then statistics that keep every activation O(1)):
   * conv kernel ~ N(0, 1/fan_in);
   * BN: gamma ~ U(0.9,1.1) (x0.5 on convs that feed a shortcut), beta ~ N(0,0.1),
-        moving_mean ~ N(0,0.05), moving_variance ~ 0.505*U(0.9,1.1)
-        (0.505 = E[leaky_0.1(z)^2] for z~N(0,1): the second moment arriving at the next conv);
-  * head convs (linear + bias): kernel ~ N(0, head_std^2/(0.505*fan_in)), bias ~ N(0,0.5), with the
-    objectness channels shifted by ``obj_bias`` to set the candidate density after thresholding.
+        moving_mean = m + N(0,0.05)*sqrt(v), moving_variance = v*U(0.9,1.1), where (m, v) is the
+        measured mean/variance of that conv's pre-BN output over all channels and pixels.  A naive
+        init with unit statistics lets the 23-block residual trunk grow to rms ~40 and saturates the
+        heads; TF's default (glorot, identity BN) collapses to 0.  The (m, v) pairs are ~100 scalars
+        per network measured once with the fp32 CPU oracle on seed-2 kernels
+        (oracle/calibrate_synth.py -> synth_calib.json, keyed by the BN-conv shape list); networks
+        without a table fall back to (0, 0.505);
+  * head convs (linear + bias): kernel ~ N(0, head_std^2/(m2*fan_in)) with m2 the measured second
+    moment of the head's input, bias ~ N(0,0.5), objectness channels shifted by ``obj_bias`` to set
+    the candidate density after thresholding.
 """
+import json
+import os
+
 import numpy as np
 
 from . import plan as _plan
 
 
-def weight_stream(plan, seed=2, num_classes=80, head_std=1.5, obj_bias=-4.0):
-    """float32 stream in darknet order for ``plan`` (list of LayerSpec)."""
+def _signature(plan):
+    return "|".join("{}-{}-{}".format(cin, cout, k) for _, cin, cout, k, bn, _, _ in _plan.conv_specs(plan) if bn)
+
+
+_calib_cache = None
+
+
+def load_calibration(plan):
+    """{'bn': [[mean, var], ...] per BN conv, 'head_m2': [...] per head conv} or None."""
+    global _calib_cache
+    if _calib_cache is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth_calib.json")
+        _calib_cache = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                for entry in json.load(f)["tables"]:
+                    _calib_cache[entry["signature"]] = entry
+    return _calib_cache.get(_signature(plan))
+
+
+def weight_stream(plan, seed=2, num_classes=80, head_std=1.5, obj_bias=-4.0, calib="auto"):
+    """float32 stream in darknet order for ``plan`` (list of LayerSpec).  ``calib``: "auto" (table lookup),
+    None (unit statistics) or an explicit table dict."""
+    if isinstance(calib, str):
+        calib = load_calibration(plan)
     rng = np.random.RandomState(seed)
     chunks = []
+    i_bn = i_head = 0
     for _, cin, cout, k, bn, feeds_shortcut, is_head in _plan.conv_specs(plan):
         fan_in = cin * k * k
         if bn:
+            m, v = (calib["bn"][i_bn] if calib else (0.0, 0.505))
+            i_bn += 1
             gamma = rng.uniform(0.9, 1.1, cout) * (0.5 if feeds_shortcut else 1.0)
             beta = rng.normal(0.0, 0.1, cout)
-            mean = rng.normal(0.0, 0.05, cout)
-            var = 0.505 * rng.uniform(0.9, 1.1, cout)
+            mean = m + rng.normal(0.0, 0.05, cout) * np.sqrt(v)
+            var = v * rng.uniform(0.9, 1.1, cout)
             chunks += [beta, gamma, mean, var]
             kernel = rng.standard_normal(cout * fan_in) * np.sqrt(1.0 / fan_in)
         else:
+            m2 = (calib["head_m2"][i_head] if calib else 0.505)
+            i_head += 1
             bias = rng.normal(0.0, 0.5, cout)
             per_anchor = 5 + num_classes
             if cout % per_anchor == 0:
                 bias[4::per_anchor] += obj_bias
             chunks.append(bias)
-            kernel = rng.standard_normal(cout * fan_in) * (head_std / np.sqrt(0.505 * fan_in))
+            kernel = rng.standard_normal(cout * fan_in) * (head_std / np.sqrt(m2 * fan_in))
         chunks.append(kernel)
     return np.concatenate(chunks).astype(np.float32)
 
