@@ -146,6 +146,26 @@ int yb_engine_set_conv_impl(yb_engine* e, int impl);
 /* number of kernel launches the last forward / detect enqueued */
 int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches);
 
+/* ---- pipelining, timing and introspection (used by bench.py; optional for integrators) ---- */
+/* Records device event `idx` (0..7) on the engine's stream / returns the device time between two marks
+ * (synchronises on `to`).  This is how the bench times K steps on the stream the kernels run on. */
+int yb_engine_mark(yb_engine* e, int idx);
+int yb_engine_elapsed(yb_engine* e, int from, int to, float* ms);
+/* After yb_engine_detect_async: enqueue the copy of the results into caller (ideally pinned) host buffers
+ * without waiting; yb_engine_fetch_wait(slot) blocks until that copy is complete.  Two slots allow the
+ * caller to overlap step i+1 (including its H2D image copy, which runs on a separate copy stream) with
+ * the consumption of step i. */
+int yb_engine_fetch_async(yb_engine* e, yb_det* out, int* counts, int max_per_image, int slot);
+int yb_engine_fetch_wait(yb_engine* e, int slot);
+/* Per-op CUDA-event timing inside yb_engine_forward: enable, run forwards, then read the summed
+ * milliseconds per launched op (layer_idx = plan entry that op implements) over n_forwards forwards. */
+int yb_engine_profiling(yb_engine* e, int enable);
+int yb_engine_profile_read(yb_engine* e, int* layer_idx, float* ms_sum, int cap, int* n_ops, int* n_forwards);
+/* Describes launched op `op_index`: path 0 = tcgen05 conv, 1 = direct first conv, 2 = CUDA-core conv,
+ * negative = non-conv kernel; tile shape; algorithmic FLOPs per image (2*MAC). */
+int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn_tile, int* bk, int* stages,
+                      double* flops_per_image);
+
 /* ---- stand-alone post-processing on caller tensors ---- */
 typedef struct yb_scale {
   int h, w, n_anchors;

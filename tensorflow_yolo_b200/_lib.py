@@ -58,6 +58,15 @@ _SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int)]),
     "yb_engine_set_conv_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_launch_count": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int), _P(ctypes.c_int)]),
+    "yb_engine_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_engine_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
+    "yb_engine_fetch_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "yb_engine_fetch_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_engine_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_engine_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              _P(ctypes.c_int), _P(ctypes.c_int)]),
+    "yb_engine_op_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_int),
+                                         _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_double)]),
     "yb_post_create": (ctypes.c_int, [_P(yb_scale), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _P(ctypes.c_void_p)]),
     "yb_post_destroy": (None, [ctypes.c_void_p]),

@@ -270,7 +270,15 @@ struct yb_engine {
   int rows = 0, box_len = 0;
   char* arena = nullptr;
   size_t arena_bytes = 0;
-  void* input_dev = nullptr;      // staging for host images (max_batch*H*W*C floats)
+  void* input_dev[2] = {nullptr, nullptr};   // double-buffered staging for host images
+  cudaStream_t copy_stream = nullptr;        // H2D of batch i+1 overlaps the compute of batch i
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_input_free[2] = {nullptr, nullptr};
+  int stage_toggle = 0;
+  int last_input_reader = 0;                 // index of the last op that reads the network input
+  cudaEvent_t marks[8] = {nullptr};
+  cudaEvent_t ev_fetch[2] = {nullptr, nullptr};
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;      // (n_ops + 1) per profiled forward
   const void* cur_input = nullptr;
   int cur_input_dtype = YB_F32;
   float* d_u8_lut = nullptr;
@@ -717,7 +725,17 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
       YB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
       YB_CUDA(cudaMalloc(&e->arena, e->arena_bytes));
       YB_CUDA(cudaMemset(e->arena, 0, e->arena_bytes));
-      YB_CUDA(cudaMalloc(&e->input_dev, (size_t)max_batch * in_h * in_w * in_c * 4));
+      YB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        YB_CUDA(cudaMalloc(&e->input_dev[i], (size_t)max_batch * in_h * in_w * in_c * 4));
+        YB_CUDA(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+        YB_CUDA(cudaEventCreateWithFlags(&e->ev_input_free[i], cudaEventDisableTiming));
+        YB_CUDA(cudaEventCreateWithFlags(&e->ev_fetch[i], cudaEventDisableTiming));
+      }
+      for (int i = 0; i < 8; ++i) YB_CUDA(cudaEventCreate(&e->marks[i]));
+      e->last_input_reader = 0;
+      for (size_t i = 0; i < e->ops.size(); ++i)
+        if (e->ops[i].in.buf == -2 || e->ops[i].in2.buf == -2) e->last_input_reader = (int)i;
       float lut[256];
       for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);   // image / 255. (net/base.py:153) then the fp32 feed cast
       YB_CUDA(cudaMalloc(&e->d_u8_lut, sizeof(lut)));
@@ -738,8 +756,17 @@ void yb_engine_destroy(yb_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (Op& op : e->ops) { cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift); }
-  cudaFree(e->arena); cudaFree(e->input_dev); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  cudaFree(e->arena); cudaFree(e->input_dev[0]); cudaFree(e->input_dev[1]); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
   e->post.release();
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    if (e->ev_input_free[i]) cudaEventDestroy(e->ev_input_free[i]);
+    if (e->ev_fetch[i]) cudaEventDestroy(e->ev_fetch[i]);
+  }
+  for (int i = 0; i < 8; ++i) if (e->marks[i]) cudaEventDestroy(e->marks[i]);
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -811,22 +838,38 @@ static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, in
   if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_forward before yb_engine_load_weights");
   YB_TRY(set_device(e->device));
   const size_t bytes = (size_t)n * e->H * e->W * e->C * (dtype == YB_F32 ? 4 : 1);
+  int slot = -1;
   if (mem == YB_MEM_HOST) {
-    YB_CUDA(cudaMemcpyAsync(e->input_dev, images, bytes, cudaMemcpyHostToDevice, e->stream));
-    e->cur_input = e->input_dev;
+    // staging[slot] may still be read by the first conv of the forward before last: wait for it, copy on the
+    // copy stream (overlaps whatever the compute stream is doing), then make the compute stream wait for the copy
+    slot = e->stage_toggle;
+    e->stage_toggle ^= 1;
+    YB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_input_free[slot], 0));
+    YB_CUDA(cudaMemcpyAsync(e->input_dev[slot], images, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    YB_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+    YB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    e->cur_input = e->input_dev[slot];
   } else {
     e->cur_input = images;
   }
   e->cur_input_dtype = dtype;
   e->fwd_launches = 0;
+  std::vector<cudaEvent_t> own;
+  if (!evs && e->prof_on) {
+    own.resize(e->ops.size() + 1);
+    for (auto& ev : own) YB_CUDA(cudaEventCreate(&ev));
+    e->prof_events.insert(e->prof_events.end(), own.begin(), own.end());
+    evs = own.data();
+  }
   int k = 0;
   for (Op& op : e->ops) {
     if (evs) YB_CUDA(cudaEventRecord(evs[k], e->stream));
     YB_TRY(run_op(e, op, n));
+    if (slot >= 0 && k == e->last_input_reader) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
     ++e->fwd_launches;
     ++k;
   }
-  if (evs) { YB_CUDA(cudaEventRecord(evs[k], e->stream)); *n_ev = k + 1; }
+  if (evs) { YB_CUDA(cudaEventRecord(evs[k], e->stream)); if (n_ev) *n_ev = k + 1; }
   e->last_n = n;
   e->detected = false;
   return YB_OK;
@@ -959,6 +1002,82 @@ int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_laun
   if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
   if (forward_launches) *forward_launches = e->fwd_launches;
   if (detect_launches) *detect_launches = e->det_launches;
+  return YB_OK;
+}
+
+int yb_engine_mark(yb_engine* e, int idx) {
+  if (!e || idx < 0 || idx >= 8) return fail(YB_ERR_INVALID, "yb_engine_mark: bad argument");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaEventRecord(e->marks[idx], e->stream));
+  return YB_OK;
+}
+
+int yb_engine_elapsed(yb_engine* e, int from, int to, float* ms) {
+  if (!e || !ms || from < 0 || from >= 8 || to < 0 || to >= 8) return fail(YB_ERR_INVALID, "yb_engine_elapsed: bad argument");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaEventSynchronize(e->marks[to]));
+  YB_CUDA(cudaEventElapsedTime(ms, e->marks[from], e->marks[to]));
+  return YB_OK;
+}
+
+int yb_engine_fetch_async(yb_engine* e, yb_det* out, int* counts, int max_per_image, int slot) {
+  if (!e || !out || !counts || slot < 0 || slot > 1) return fail(YB_ERR_INVALID, "yb_engine_fetch_async: bad argument");
+  if (!e->detected) return fail(YB_ERR_STATE, "yb_engine_fetch_async before yb_engine_detect_async");
+  YB_TRY(set_device(e->device));
+  if (max_per_image > e->rows) max_per_image = e->rows;
+  if (max_per_image <= 0) return fail(YB_ERR_INVALID, "max_per_image must be positive");
+  YB_TRY(e->post.gather(e->stream, e->last_n, max_per_image));
+  ++e->det_launches;
+  YB_CUDA(cudaMemcpyAsync(counts, e->post.n_keep, (size_t)e->last_n * 4, cudaMemcpyDeviceToHost, e->stream));
+  YB_CUDA(cudaMemcpyAsync(out, e->post.dets, (size_t)e->last_n * max_per_image * sizeof(DetOut), cudaMemcpyDeviceToHost, e->stream));
+  YB_CUDA(cudaEventRecord(e->ev_fetch[slot], e->stream));
+  return YB_OK;
+}
+
+int yb_engine_fetch_wait(yb_engine* e, int slot) {
+  if (!e || slot < 0 || slot > 1) return fail(YB_ERR_INVALID, "yb_engine_fetch_wait: bad argument");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaEventSynchronize(e->ev_fetch[slot]));
+  return YB_OK;
+}
+
+int yb_engine_profiling(yb_engine* e, int enable) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  e->prof_events.clear();
+  e->prof_on = enable != 0;
+  return YB_OK;
+}
+
+int yb_engine_profile_read(yb_engine* e, int* layer_idx, float* ms_sum, int cap, int* n_ops, int* n_forwards) {
+  if (!e || !layer_idx || !ms_sum || !n_ops || !n_forwards) return fail(YB_ERR_INVALID, "yb_engine_profile_read: bad argument");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  const int nops = (int)e->ops.size();
+  const int per = nops + 1;
+  const int nf = (int)e->prof_events.size() / per;
+  *n_ops = nops; *n_forwards = nf;
+  for (int i = 0; i < nops && i < cap; ++i) { ms_sum[i] = 0.f; layer_idx[i] = e->ops[i].layer; }
+  for (int f = 0; f < nf; ++f)
+    for (int i = 0; i < nops && i < cap; ++i) {
+      float t = 0.f;
+      YB_CUDA(cudaEventElapsedTime(&t, e->prof_events[f * per + i], e->prof_events[f * per + i + 1]));
+      ms_sum[i] += t;
+    }
+  return YB_OK;
+}
+
+int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn_tile, int* bk, int* stages, double* flops_per_image) {
+  if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_op_info: bad argument");
+  const Op& op = e->ops[op_index];
+  if (layer) *layer = op.layer;
+  if (path) *path = op.kind == OP_CONV ? op.path : -1 - op.kind;
+  if (bn_tile) *bn_tile = op.bn_tile;
+  if (bk) *bk = op.bk;
+  if (stages) *stages = op.stages;
+  if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin : 0.0;
   return YB_OK;
 }
 

@@ -115,6 +115,42 @@ class Engine(object):
     def sync(self):
         _lib.check(_lib.lib().yb_engine_sync(self._h))
 
+    def mark(self, idx):
+        _lib.check(_lib.lib().yb_engine_mark(self._h, idx))
+
+    def elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        _lib.check(_lib.lib().yb_engine_elapsed(self._h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    def fetch_async(self, dets, counts, slot):
+        """dets: [n, cap] DET_DTYPE array, counts: [n] int32 (ideally views of pinned memory)."""
+        _lib.check(_lib.lib().yb_engine_fetch_async(self._h, dets.ctypes.data, counts.ctypes.data, dets.shape[1], slot))
+
+    def fetch_wait(self, slot):
+        _lib.check(_lib.lib().yb_engine_fetch_wait(self._h, slot))
+
+    def profiling(self, enable):
+        _lib.check(_lib.lib().yb_engine_profiling(self._h, int(enable)))
+
+    def profile_read(self):
+        """[(plan layer, summed ms)] per launched op and the number of forwards they were summed over."""
+        cap = 4 * len(self.plan)
+        idx = np.zeros(cap, dtype=np.int32)
+        ms = np.zeros(cap, dtype=np.float32)
+        n_ops, n_fwd = ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().yb_engine_profile_read(self._h, idx.ctypes.data, ms.ctypes.data, cap,
+                                                     ctypes.byref(n_ops), ctypes.byref(n_fwd)))
+        return [(int(idx[i]), float(ms[i])) for i in range(min(n_ops.value, cap))], n_fwd.value
+
+    def op_info(self, op_index):
+        layer, path, bn, bk, st = (ctypes.c_int() for _ in range(5))
+        fl = ctypes.c_double()
+        _lib.check(_lib.lib().yb_engine_op_info(self._h, op_index, ctypes.byref(layer), ctypes.byref(path), ctypes.byref(bn),
+                                                ctypes.byref(bk), ctypes.byref(st), ctypes.byref(fl)))
+        return {"layer": layer.value, "path": path.value, "bn": bn.value, "bk": bk.value, "stages": st.value,
+                "flops_per_image": fl.value}
+
     def set_conv_impl(self, impl):
         _lib.check(_lib.lib().yb_engine_set_conv_impl(self._h, impl))
 
