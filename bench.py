@@ -244,6 +244,19 @@ def run_ours(args):
             conv_ms += ms_sum; conv_flops += info["flops_per_image"] * B * n_fwd
         else:
             other_ms += ms_sum
+    if args.dump_profile:
+        rows = []
+        for op_i, (layer, ms_sum) in enumerate(prof):
+            info = eng.op_info(op_i)
+            spec = state.graph.specs[layer]
+            fl = info["flops_per_image"] * B
+            t = ms_sum / max(n_fwd, 1)
+            rows.append({"op": op_i, "layer": layer, "kind": yplan.KIND_NAMES[spec.kind], "out_hwc": list(spec.shape),
+                         "ksize": spec.ksize, "stride": spec.stride, "cin": state.graph.specs[spec.src[0]].shape[2] if spec.src else 0,
+                         "path": info["path"], "bn": info["bn"], "bk": info["bk"], "stages": info["stages"],
+                         "ms": t, "tflops": (fl / (t * 1e-3) / 1e12) if t > 0 and fl > 0 else 0.0})
+        with open(args.dump_profile, "w") as f:
+            json.dump({"batch": B, "forwards": n_fwd, "step_ms": ms / K, "ops": rows}, f, indent=0)
     top_key, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
     achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
@@ -311,6 +324,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline pass")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-clock budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default=None, help="write the per-op CUDA-event table of the timed region (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -129,7 +129,9 @@ int yb_engine_read_layer(yb_engine* e, int layer, float* host_out, size_t capaci
 
 /* Replaces find_bounding_boxes (net/v3.py:139-151, net/v2.py:82-90) for the last forward:
  * decode + threshold + NMS on the device.  out: [n][max_per_image] detections in kept
- * (score-descending) order; counts[n].  Synchronises the engine's stream. */
+ * (score-descending) order (row stride is always max_per_image); counts[n] receives the number of kept
+ * boxes per image, which may exceed max_per_image -- then only the first max_per_image were written.
+ * Synchronises the engine's stream. */
 int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode,
                      yb_det* out, int* counts, int max_per_image);
 /* Same, but leaves the results on the device (for device-timed benches); returns after enqueueing. */

@@ -154,8 +154,7 @@ struct PostCtx {
     YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
     YB_CUDA(cudaMalloc(&order, nr * 4));
     YB_CUDA(cudaMalloc(&n_keep, (size_t)max_batch * 4)); YB_CUDA(cudaMalloc(&n_cand, (size_t)max_batch * 4));
-    dets_cap = nr;
-    YB_CUDA(cudaMalloc(&dets, nr * sizeof(DetOut)));
+    dets_cap = 0;
     for (int i = 0; i < 3; ++i) YB_CUDA(cudaEventCreate(&ev[i]));
     return YB_OK;
   }
@@ -206,8 +205,16 @@ struct PostCtx {
     return nms_launch<double, false, true>(st, n, nms_args(iou_thr, mode == YB_NMS_PER_CLASS));
   }
 
+  // out[n][max_per_image] on the device; at most min(n_keep, max_per_image) records per image are written
   int gather(cudaStream_t st, int n, int max_per_image) {
-    dim3 grid(ceil_div(max_per_image, 128), n);
+    const size_t need = (size_t)n * max_per_image;
+    if (need > dets_cap) {
+      YB_CUDA(cudaStreamSynchronize(st));
+      cudaFree(dets); dets = nullptr; dets_cap = 0;
+      YB_CUDA(cudaMalloc(&dets, need * sizeof(DetOut)));
+      dets_cap = need;
+    }
+    dim3 grid(ceil_div(std::min(max_per_image, rows), 128), n);
     gather_dets_kernel<<<grid, 128, 0, st>>>(rows, max_per_image, order, n_keep, prob, x, y, w, h, cls, dets);
     YB_CUDA(cudaGetLastError());
     return YB_OK;
@@ -943,7 +950,6 @@ int yb_engine_detect_async(yb_engine* e, float threshold, float iou_threshold, i
 
 static int copy_dets(PostCtx& post, cudaStream_t st, int n, yb_det* out, int* counts, int max_per_image, int* det_launches) {
   if (max_per_image <= 0) return fail(YB_ERR_INVALID, "max_per_image must be positive");
-  if ((size_t)n * max_per_image > post.dets_cap) max_per_image = (int)(post.dets_cap / n);
   YB_TRY(post.gather(st, n, max_per_image));
   if (det_launches) ++*det_launches;
   static_assert(sizeof(yb_det) == sizeof(DetOut), "yb_det layout");
@@ -956,7 +962,6 @@ static int copy_dets(PostCtx& post, cudaStream_t st, int n, yb_det* out, int* co
 int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode, yb_det* out, int* counts, int max_per_image) {
   if (!out || !counts) return fail(YB_ERR_INVALID, "yb_engine_detect: output buffers are NULL");
   YB_TRY(yb_engine_detect_async(e, threshold, iou_threshold, nms_mode));
-  if (max_per_image > e->rows) max_per_image = e->rows;
   return copy_dets(e->post, e->stream, e->last_n, out, counts, max_per_image, &e->det_launches);
 }
 
@@ -1024,7 +1029,6 @@ int yb_engine_fetch_async(yb_engine* e, yb_det* out, int* counts, int max_per_im
   if (!e || !out || !counts || slot < 0 || slot > 1) return fail(YB_ERR_INVALID, "yb_engine_fetch_async: bad argument");
   if (!e->detected) return fail(YB_ERR_STATE, "yb_engine_fetch_async before yb_engine_detect_async");
   YB_TRY(set_device(e->device));
-  if (max_per_image > e->rows) max_per_image = e->rows;
   if (max_per_image <= 0) return fail(YB_ERR_INVALID, "max_per_image must be positive");
   YB_TRY(e->post.gather(e->stream, e->last_n, max_per_image));
   ++e->det_launches;
@@ -1169,7 +1173,6 @@ int yb_post_run(yb_post* p, const float* head, int mem, int n, float threshold, 
   YB_CUDA(cudaEventRecord(p->ctx.ev[2], p->stream));
   p->timed = true;
   if (out && counts) {
-    if (max_per_image > p->ctx.rows) max_per_image = p->ctx.rows;
     YB_TRY(copy_dets(p->ctx, p->stream, n, out, counts, max_per_image, nullptr));
   }
   if (cand_counts) {
@@ -1197,7 +1200,6 @@ int yb_post_decode(yb_post* p, const float* head, int mem, int n, float threshol
   YB_TRY(post_stage_and_decode(p, head, mem, n, threshold));
   list_candidates_kernel<<<n, 32, 0, p->stream>>>(p->ctx.rows, p->ctx.prob, p->ctx.order, p->ctx.n_keep);
   YB_CUDA(cudaGetLastError());
-  if (max_per_image > p->ctx.rows) max_per_image = p->ctx.rows;
   return copy_dets(p->ctx, p->stream, n, out, counts, max_per_image, nullptr);
 }
 
