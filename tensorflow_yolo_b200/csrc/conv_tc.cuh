@@ -380,4 +380,259 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ================================================================================================
+// Persistent variant: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers let the
+// epilogue of tile i (TMEM -> registers -> global) overlap the mainloop of tile i+1, the TMA producer
+// runs ahead across tile boundaries, and the per-CTA fixed costs (TMEM alloc, barrier init, descriptor
+// prefetch, scale/shift staging) are paid once per SM instead of once per tile.
+//   warp 0        TMA producer (one elected lane)
+//   warp 1        MMA issuer (one elected lane) + TMEM owner
+//   warps 2..9    epilogue: TMEM lane quarter = warp % 4; the two warps of a quarter split the columns
+// ================================================================================================
+constexpr int CONV_TCP_THREADS = 320;
+constexpr int CONV_TCP_EPI_WARPS = 8;
+
+template <int BN, int BK, int STAGES>
+struct ConvTcpSmem {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int SS_OFFSET = BAR_OFFSET + (2 * STAGES + 4 + 1) * 8;
+  static constexpr int MAX_COUT_PAD = 1024;
+  static constexpr int TOTAL = SS_OFFSET + 2 * MAX_COUT_PAD * 4 + 1024;
+};
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
+                       const int n_tiles_n, const int n_tiles, const int cout_pad) {
+  using L = ConvTcpSmem<BN, BK, STAGES>;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFFSET);
+  float* s_shift = s_scale + L::MAX_COUT_PAD;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k = a.taps * a.kc_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], CONV_TCP_EPI_WARPS);
+    }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  }
+  for (int i = threadIdx.x; i < cout_pad; i += CONV_TCP_THREADS) {
+    s_scale[i] = a.scale[i];
+    s_shift[i] = a.shift[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = a.Ho * a.Wo;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_m = tile / n_tiles_n;
+        const int n0 = (tile - tile_m * n_tiles_n) * BN;
+        const int m0 = tile_m * 128;
+        int img = 0, base_w = 0, base_h = 0;
+        if (a.im2col) {
+          img = m0 / hw;
+          const int rem = m0 - img * hw;
+          const int p0 = rem / a.Wo;
+          base_w = (rem - p0 * a.Wo) * a.conv_stride - a.pad;
+          base_h = p0 * a.conv_stride - a.pad;
+        }
+        int tap = 0, cb = 0, kh = 0, kw = 0;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+          else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+          tma_load_2d(&tmB, &full_bar[stage], sa + L::A_BYTES, kb * BK, n0);
+          if (++cb == a.kc_blocks) { cb = 0; ++tap; if (++kw == a.ksize) { kw = 0; ++kh; } }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc<BN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t da = make_kmajor_desc<BK>(sa);
+          const uint64_t db = make_kmajor_desc<BK>(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                 // 0 or 1
+    constexpr int NCH = BN / 32;                      // 32-column chunks per tile
+    constexpr int CH_PER = (NCH + 1) / 2;
+    const int ch_begin = half * CH_PER;
+    const int ch_end = (ch_begin + CH_PER < NCH) ? ch_begin + CH_PER : NCH;
+    const int hw = a.Ho * a.Wo;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int tile_m = tile / n_tiles_n;
+      const int n0 = (tile - tile_m * n_tiles_n) * BN;
+      const int m = tile_m * 128 + quarter * 32 + lane;
+      const bool valid = m < a.M;
+      long long opix[4];
+      int n_dst = 1, ch_extra = 0;
+      if (a.out_mode == OUT_PLAIN) {
+        opix[0] = m;
+      } else {
+        const int img = m / hw;
+        const int rem = m - img * hw;
+        const int p = rem / a.Wo;
+        const int q = rem - p * a.Wo;
+        if (a.out_mode == OUT_UPSAMPLE2) {
+          const long long W2 = 2 * a.Wo;
+          const long long base = ((long long)img * 2 * a.Ho + 2 * p) * W2 + 2 * q;
+          opix[0] = base; opix[1] = base + 1; opix[2] = base + W2; opix[3] = base + W2 + 1;
+          n_dst = 4;
+        } else {
+          opix[0] = ((long long)img * (a.Ho >> 1) + (p >> 1)) * (a.Wo >> 1) + (q >> 1);
+          ch_extra = ((p & 1) * 2 + (q & 1)) * a.cout;
+        }
+      }
+      // residual of the first chunk is requested before waiting for the accumulator
+      uint4 rnext[4];
+      const bool has_res = a.res != nullptr;
+      auto load_res = [&](int chunk, uint4 (&r)[4]) {
+        const int cbase = n0 + chunk * 32;
+        const __nv_bfloat16* rp = a.res + (long long)m * a.res_ld + cbase;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (valid && cbase + g * 8 < a.cout) r[g] = __ldg(reinterpret_cast<const uint4*>(rp + g * 8));
+          else r[g] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (has_res && ch_begin < ch_end) load_res(ch_begin, rnext);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = ch_begin; chunk < ch_end; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
+        uint4 rcur[4];
+        if (has_res) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+          if (chunk + 1 < ch_end) load_res(chunk + 1, rnext);
+        }
+        tmem_ld_wait();
+        const int cbase = n0 + chunk * 32;
+        if (valid && cbase < a.cout) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = __uint_as_float(v[j]) * s_scale[cbase + j] + s_shift[cbase + j];
+            if (a.leaky) y = fmaxf(y, 0.1f * y);
+            f[j] = y;
+          }
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t rw[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (a.out_f32) {
+            float* op = reinterpret_cast<float*>(a.out) + opix[0] * a.out_ld + cbase;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (cbase + g * 4 < a.out_ld)
+                *reinterpret_cast<float4*>(op + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            }
+          } else {
+            uint4 pk[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+              pk[g].x = *reinterpret_cast<uint32_t*>(&b0);
+              pk[g].y = *reinterpret_cast<uint32_t*>(&b1);
+              pk[g].z = *reinterpret_cast<uint32_t*>(&b2);
+              pk[g].w = *reinterpret_cast<uint32_t*>(&b3);
+            }
+            for (int d = 0; d < n_dst; ++d) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + opix[d] * a.out_ld + ch_extra + cbase;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (cbase + g * 8 < a.cout) *reinterpret_cast<uint4*>(op + g * 8) = pk[g];
+              }
+            }
+          }
+        }
+      }
+      // this warp has finished reading the accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace yb

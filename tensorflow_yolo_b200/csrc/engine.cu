@@ -269,6 +269,8 @@ struct yb_engine {
   int H = 0, W = 0, C = 0, max_batch = 0, decode_mode = 0, num_classes = 0;
   bool keep_all = false;
   int bn_max = 128;
+  bool persistent = true;
+  int num_sms = 148;
   std::vector<Shape> shape;
   std::vector<View> view;
   std::vector<Buf> bufs;
@@ -319,6 +321,32 @@ static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
   return YB_OK;
 }
 
+template <int BN, int BK, int ST>
+static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms) {
+  using L = ConvTcpSmem<BN, BK, ST>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget");
+  auto kern = conv_tc_persist_kernel<BN, BK, ST>;
+  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  const int tiles_m = ceil_div(a.M, 128);
+  const int tiles_n = op.cout_pad / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int grid = std::min(n_tiles, num_sms);
+  kern<<<grid, CONV_TCP_THREADS, L::TOTAL, st>>>(op.tmA, op.tmB, a, tiles_n, n_tiles, op.cout_pad);
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// persistent kernel: pipeline depth fills the shared memory left after the scale/shift staging
+static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms) {
+  if (op.cout_pad > 1024) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
+#define YB_CASE(BN_, BK_, ST_) \
+  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, ST_>(st, op, a, num_sms);
+  YB_CASE(256, 64, 4) YB_CASE(128, 64, 6) YB_CASE(64, 64, 8) YB_CASE(32, 64, 8)
+  YB_CASE(128, 32, 8) YB_CASE(64, 32, 8) YB_CASE(32, 32, 8)
+#undef YB_CASE
+  return fail(YB_ERR_INVALID, "no persistent tcgen05 conv instantiation for BN=%d BK=%d", op.bn_tile, op.bk);
+}
+
 static int stages_for(int bn, int bk) {
   // env override for tuning; defaults keep two CTAs resident per SM where the tile allows it
   const char* s = getenv("YB_STAGES");
@@ -358,7 +386,8 @@ static int run_op(yb_engine* e, Op& op, int n) {
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      YB_TRY(dispatch_conv_tc(st, op, a));
+      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms));
+      else YB_TRY(dispatch_conv_tc(st, op, a));
     } else if (path == PATH_DIRECT) {
       const int smem = a.taps * op.cin * 32 * 4;
       dim3 grid(ceil_div(a.M, 128), ceil_div(op.cout, 32));
@@ -724,6 +753,10 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   e->plan.assign(plan, plan + n_layers);
   const char* ka = getenv("YB_KEEP_ALL");
   e->keep_all = ka && atoi(ka) != 0;
+  const char* ps = getenv("YB_PERSIST");
+  if (ps) e->persistent = atoi(ps) != 0;
+  if (e->persistent) e->bn_max = 256;
+  cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
   const char* bm = getenv("YB_BN_MAX");
   if (bm && (atoi(bm) == 32 || atoi(bm) == 64 || atoi(bm) == 128 || atoi(bm) == 256)) e->bn_max = atoi(bm);
   int r = compile_plan(e);
