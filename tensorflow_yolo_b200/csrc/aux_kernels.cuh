@@ -129,6 +129,135 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const InView in, const
   }
 }
 
+// ---- first conv on tensor cores: 3x3, Cin=3 (K = 27 padded to 32), Cout = 32 per blockIdx.y ----
+// The layer is HBM-bound (AI ~25 flop/B) and K is only 27, so the A operand (im2col rows) is gathered
+// straight from the L1-cached image into mma.sync fragments: each warp owns 16 consecutive output pixels
+// (m16), two k16 steps, four n8 tiles.  Thread (g = lane/4, t = lane%4) holds rows g and g+8 and the k
+// columns {2t, 2t+1, 2t+8, 2t+9} (+16 for the second step); their (dy, dx, ci) offsets are loop-invariant.
+// Epilogue: scale/shift/leaky, a 4x4 transpose inside each quad so that every thread stores 16 bytes.
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool U8>
+__global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                             const float* __restrict__ u8_lut, int n_mtiles) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int c0 = blockIdx.y * 32;
+  const int K = 27;
+  // k columns of this thread: j = 0..7 -> k = (j>>2)*16 + ((j>>1)&1)*8 + 2t + (j&1)
+  int koff[8];       // offset (in elements) relative to the output pixel's own input position, or INT_MIN if k >= 27
+  int kdy[8], kdx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
+    const int tap = k / 3, ci = k - tap * 3;
+    kdy[j] = (k < K) ? tap / 3 - 1 : 99;
+    kdx[j] = tap % 3 - 1;
+    koff[j] = (kdy[j] * in.W + kdx[j]) * in.ld + ci;
+  }
+  // B fragments: b[ks][nt][0] = {W[ks*16+2t][n], W[ks*16+2t+1][n]}, [1] = rows +8,+9 ; n = c0 + nt*8 + g
+  uint32_t bf[2][4][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ks * 16 + h * 8 + 2 * t;
+        const int n = c0 + nt * 8 + g;
+        const float w0 = (k < K) ? wt[(long long)k * a.cout + n] : 0.0f;
+        const float w1 = (k + 1 < K) ? wt[(long long)(k + 1) * a.cout + n] : 0.0f;
+        bf[ks][nt][h] = pack_bf16(w0, w1);
+      }
+  // epilogue constants of the 8 channels this thread finally stores: c0 + 8t .. c0 + 8t + 7
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = a.scale[c0 + 8 * t + j]; sh[j] = a.shift[c0 + 8 * t + j]; }
+
+  const int hw = in.H * in.W;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int mt = warp_global; mt < n_mtiles; mt += n_warps) {
+    uint32_t afrag[2][4];
+    bool rvalid[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int m = mt * 16 + g + r * 8;
+      rvalid[r] = m < a.M;
+      const int mm = rvalid[r] ? m : 0;
+      const int img = mm / hw, rem = mm - img * hw;
+      const int y = rem / in.W, x = rem - y * in.W;
+      const long long base = (long long)mm * in.ld;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int yy = y + kdy[j], xx = x + kdx[j];
+        const bool ok = rvalid[r] && yy >= 0 && yy < in.H && xx >= 0 && xx < in.W;
+        float val = 0.0f;
+        if (ok) {
+          if (U8) val = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[base + koff[j]]];
+          else val = __ldg(reinterpret_cast<const float*>(in.ptr) + base + koff[j]);
+        }
+        v[j] = val;
+      }
+      // fragment order: a0:(row g, k 2t..), a1:(row g+8, same), a2:(row g, k +8), a3:(row g+8, k +8)
+      afrag[0][r] = pack_bf16(v[0], v[1]);
+      afrag[0][r + 2] = pack_bf16(v[2], v[3]);
+      afrag[1][r] = pack_bf16(v[4], v[5]);
+      afrag[1][r + 2] = pack_bf16(v[6], v[7]);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
+    // acc[nt][0..1] = (row g, channels nt*8 + 2t, +1); acc[nt][2..3] = (row g+8, same channels).
+    // Quad transpose: thread t ends up with n-tile t's eight channels (pairs from lanes 0..3 of the quad).
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float o[8];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        // lane s sends the pair of n-tile (s + rr) & 3; lane t receives from s = (t - rr) & 3 -> n-tile t
+        const int nts = (t + rr) & 3;
+        float s0 = nts == 0 ? acc[0][2 * r] : nts == 1 ? acc[1][2 * r] : nts == 2 ? acc[2][2 * r] : acc[3][2 * r];
+        float s1 = nts == 0 ? acc[0][2 * r + 1] : nts == 1 ? acc[1][2 * r + 1] : nts == 2 ? acc[2][2 * r + 1] : acc[3][2 * r + 1];
+        const int src = (lane & ~3) | ((t - rr) & 3);
+        s0 = __shfl_sync(0xffffffffu, s0, src);
+        s1 = __shfl_sync(0xffffffffu, s1, src);
+        const int s = (t - rr) & 3;          // the sender's t: its pair covers channels 2s, 2s+1 of the n-tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q == s) { o[2 * q] = s0; o[2 * q + 1] = s1; }
+      }
+      if (rvalid[r]) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float y0 = o[2 * q] * sc[2 * q] + sh[2 * q];
+          float y1 = o[2 * q + 1] * sc[2 * q + 1] + sh[2 * q + 1];
+          if (a.leaky) { y0 = fmaxf(y0, 0.1f * y0); y1 = fmaxf(y1, 0.1f * y1); }
+          pk[q] = pack_bf16(y0, y1);
+        }
+        const int m = mt * 16 + g + r * 8;
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)m * a.out_ld + c0 + 8 * t;
+        *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
 // ---- plain CUDA-core conv on the packed bf16 operands: wt [cout_pad][taps*Cin] ----
 // one thread = one output pixel x 4 output channels
 __global__ void __launch_bounds__(256) conv_simt_kernel(const InView in, const __nv_bfloat16* __restrict__ wt, const ConvArgs a) {

@@ -389,6 +389,18 @@ static int run_op(yb_engine* e, Op& op, int n) {
       if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms));
       else YB_TRY(dispatch_conv_tc(st, op, a));
     } else if (path == PATH_DIRECT) {
+      const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
+      const bool mma_ok = op.ksize == 3 && op.cin == 3 && op.stride == 1 && op.cout % 32 == 0 && !op.out.f32 && !op.has_res &&
+                          op.out_mode == OUT_PLAIN && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
+                          (long long)a.M * op.in.ld < (1ll << 31);
+      if (mma_ok) {
+        const int n_mtiles = ceil_div(a.M, 16);
+        dim3 grid(std::min(ceil_div(n_mtiles, 8), e->num_sms * 8), op.cout / 32);
+        if (u8) conv_first_mma_kernel<true><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_mtiles);
+        else conv_first_mma_kernel<false><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_mtiles);
+        YB_CUDA(cudaGetLastError());
+        return YB_OK;
+      }
       const int smem = a.taps * op.cin * 32 * 4;
       dim3 grid(ceil_div(a.M, 128), ceil_div(op.cout, 32));
       if (e->cur_input_dtype == YB_U8 && op.in.buf == -2)
