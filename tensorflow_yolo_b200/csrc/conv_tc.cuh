@@ -391,43 +391,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ================================================================================================
 constexpr int CONV_TCP_THREADS = 320;
 constexpr int CONV_TCP_EPI_WARPS = 8;
+constexpr int CONV_TCP_MAX_STAGES = 16;
+constexpr int CONV_TCP_MAX_COUT_PAD = 1024;
+// dynamic shared memory: [1024 B barriers | scale,shift (8 KB) | optional stationary B | stages]
+constexpr int CONV_TCP_HEADER = 1024 + 2 * CONV_TCP_MAX_COUT_PAD * 4;
+constexpr int CONV_TCP_SMEM_MAX = 232448;                             // 227 KB opt-in limit
+constexpr int CONV_TCP_TILE_BUDGET = CONV_TCP_SMEM_MAX - 1024 - CONV_TCP_HEADER;
 
-template <int BN, int BK, int STAGES>
-struct ConvTcpSmem {
-  static constexpr int A_BYTES = 128 * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
-  static constexpr int SS_OFFSET = BAR_OFFSET + (2 * STAGES + 4 + 1) * 8;
-  static constexpr int MAX_COUT_PAD = 1024;
-  static constexpr int TOTAL = SS_OFFSET + 2 * MAX_COUT_PAD * 4 + 1024;
+struct PersistArgs {
+  int n_tiles_n, n_tiles, cout_pad;
+  int n_stages;        // pipeline depth (runtime: fills the shared memory that is left)
+  int b_stationary;    // 1: the whole [BN x K] weight matrix is loaded once per CTA and stays in shared memory
 };
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
-                       const int n_tiles_n, const int n_tiles, const int cout_pad) {
-  using L = ConvTcpSmem<BN, BK, STAGES>;
+                       const PersistArgs pa) {
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;    // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFFSET);
-  float* s_shift = s_scale + L::MAX_COUT_PAD;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + CONV_TCP_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + CONV_TCP_MAX_STAGES;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                 // [2]
+  uint64_t* b_full_bar = tmem_empty_bar + 2;                    // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);
+  float* s_shift = s_scale + CONV_TCP_MAX_COUT_PAD;
+  const int num_k = a.taps * a.kc_blocks;
+  const int n_stages = pa.n_stages;
+  const bool bstat = pa.b_stationary != 0;
+  uint8_t* b_stat = smem + CONV_TCP_HEADER;                                   // num_k * B_BYTES when stationary
+  uint8_t* stages = b_stat + (bstat ? num_k * B_BYTES : 0);
+  const int stage_bytes = A_BYTES + (bstat ? 0 : B_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k = a.taps * a.kc_blocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -435,11 +442,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], CONV_TCP_EPI_WARPS);
     }
+    mbar_init(b_full_bar, 1);
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   }
-  for (int i = threadIdx.x; i < cout_pad; i += CONV_TCP_THREADS) {
+  for (int i = threadIdx.x; i < pa.cout_pad; i += CONV_TCP_THREADS) {
     s_scale[i] = a.scale[i];
     s_shift[i] = a.shift[i];
   }
@@ -451,12 +459,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
+      if (bstat) {
+        mbar_expect_tx(b_full_bar, (uint32_t)(num_k * B_BYTES));
+        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, b_full_bar, b_stat + kb * B_BYTES, kb * BK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       const int hw = a.Ho * a.Wo;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int tile_m = tile / n_tiles_n;
-        const int n0 = (tile - tile_m * n_tiles_n) * BN;
+      for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
+        const int tile_m = tile / pa.n_tiles_n;
+        const int n0 = (tile - tile_m * pa.n_tiles_n) * BN;
         const int m0 = tile_m * 128;
         int img = 0, base_w = 0, base_h = 0;
         if (a.im2col) {
@@ -466,16 +478,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           base_w = (rem - p0 * a.Wo) * a.conv_stride - a.pad;
           base_h = p0 * a.conv_stride - a.pad;
         }
-        int tap = 0, cb = 0, kh = 0, kw = 0;
+        int cb = 0, kh = 0, kw = 0;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          uint8_t* sa = stages + stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
           else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
-          tma_load_2d(&tmB, &full_bar[stage], sa + L::A_BYTES, kb * BK, n0);
-          if (++cb == a.kc_blocks) { cb = 0; ++tap; if (++kw == a.ksize) { kw = 0; ++kh; } }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (!bstat) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+          if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -485,7 +497,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (bstat) {
+      mbar_wait(b_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t b_stat_addr = smem_u32(b_stat);
+    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
@@ -495,16 +512,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sa = smem_u32(stages + stage * stage_bytes);
           const uint64_t da = make_kmajor_desc<BK>(sa);
-          const uint64_t db = make_kmajor_desc<BK>(sa + L::A_BYTES);
+          const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)(kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -517,11 +534,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int ch_end = (ch_begin + CH_PER < NCH) ? ch_begin + CH_PER : NCH;
     const int hw = a.Ho * a.Wo;
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int tile_m = tile / n_tiles_n;
-      const int n0 = (tile - tile_m * n_tiles_n) * BN;
+      const int tile_m = tile / pa.n_tiles_n;
+      const int n0 = (tile - tile_m * pa.n_tiles_n) * BN;
       const int m = tile_m * 128 + quarter * 32 + lane;
       const bool valid = m < a.M;
       long long opix[4];

@@ -270,6 +270,7 @@ struct yb_engine {
   bool keep_all = false;
   int bn_max = 128;
   bool persistent = true;
+  bool b_stationary = true;
   int num_sms = 148;
   std::vector<Shape> shape;
   std::vector<View> view;
@@ -321,28 +322,37 @@ static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
   return YB_OK;
 }
 
-template <int BN, int BK, int ST>
-static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms) {
-  using L = ConvTcpSmem<BN, BK, ST>;
-  static_assert(L::TOTAL <= 232448, "shared memory budget");
-  auto kern = conv_tc_persist_kernel<BN, BK, ST>;
-  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+template <int BN, int BK>
+static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat) {
+  auto kern = conv_tc_persist_kernel<BN, BK>;
+  const int a_bytes = 128 * BK * 2, b_bytes = BN * BK * 2;
+  const int num_k = a.taps * a.kc_blocks;
+  PersistArgs pa;
   const int tiles_m = ceil_div(a.M, 128);
-  const int tiles_n = op.cout_pad / BN;
-  const int n_tiles = tiles_m * tiles_n;
-  const int grid = std::min(n_tiles, num_sms);
-  kern<<<grid, CONV_TCP_THREADS, L::TOTAL, st>>>(op.tmA, op.tmB, a, tiles_n, n_tiles, op.cout_pad);
+  pa.n_tiles_n = op.cout_pad / BN;
+  pa.n_tiles = tiles_m * pa.n_tiles_n;
+  pa.cout_pad = op.cout_pad;
+  // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
+  const long long b_total = (long long)num_k * b_bytes;
+  pa.b_stationary = (allow_bstat && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= CONV_TCP_TILE_BUDGET) ? 1 : 0;
+  const int stage_bytes = a_bytes + (pa.b_stationary ? 0 : b_bytes);
+  const int avail = CONV_TCP_TILE_BUDGET - (pa.b_stationary ? (int)b_total : 0);
+  pa.n_stages = std::min(CONV_TCP_MAX_STAGES, avail / stage_bytes);
+  if (pa.n_stages < 2) return fail(YB_ERR_INVALID, "persistent conv: shared memory too small for BN=%d BK=%d", BN, BK);
+  const int smem = 1024 + CONV_TCP_HEADER + (pa.b_stationary ? (int)b_total : 0) + pa.n_stages * stage_bytes;
+  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = std::min(pa.n_tiles, num_sms);
+  kern<<<grid, CONV_TCP_THREADS, smem, st>>>(op.tmA, op.tmB, a, pa);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
 
-// persistent kernel: pipeline depth fills the shared memory left after the scale/shift staging
-static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms) {
-  if (op.cout_pad > 1024) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
-#define YB_CASE(BN_, BK_, ST_) \
-  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, ST_>(st, op, a, num_sms);
-  YB_CASE(256, 64, 4) YB_CASE(128, 64, 6) YB_CASE(64, 64, 8) YB_CASE(32, 64, 8)
-  YB_CASE(128, 32, 8) YB_CASE(64, 32, 8) YB_CASE(32, 32, 8)
+static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat) {
+  if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
+#define YB_CASE(BN_, BK_) \
+  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_>(st, op, a, num_sms, allow_bstat);
+  YB_CASE(256, 64) YB_CASE(128, 64) YB_CASE(64, 64) YB_CASE(32, 64)
+  YB_CASE(128, 32) YB_CASE(64, 32) YB_CASE(32, 32)
 #undef YB_CASE
   return fail(YB_ERR_INVALID, "no persistent tcgen05 conv instantiation for BN=%d BK=%d", op.bn_tile, op.bk);
 }
@@ -386,7 +396,7 @@ static int run_op(yb_engine* e, Op& op, int n) {
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms));
+      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary));
       else YB_TRY(dispatch_conv_tc(st, op, a));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
@@ -768,6 +778,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   const char* ps = getenv("YB_PERSIST");
   if (ps) e->persistent = atoi(ps) != 0;
   if (e->persistent) e->bn_max = 256;
+  const char* bs = getenv("YB_BSTAT");
+  if (bs) e->b_stationary = atoi(bs) != 0;
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
   const char* bm = getenv("YB_BN_MAX");
   if (bm && (atoi(bm) == 32 || atoi(bm) == 64 || atoi(bm) == 128 || atoi(bm) == 256)) e->bn_max = atoi(bm);
