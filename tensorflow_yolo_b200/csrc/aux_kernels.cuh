@@ -129,12 +129,13 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const InView in, const
   }
 }
 
-// ---- first conv on tensor cores: 3x3, Cin=3 (K = 27 padded to 32), Cout = 32 per blockIdx.y ----
-// The layer is HBM-bound (AI ~25 flop/B) and K is only 27, so the A operand (im2col rows) is gathered
-// straight from the L1-cached image into mma.sync fragments: each warp owns 16 consecutive output pixels
-// (m16), two k16 steps, four n8 tiles.  Thread (g = lane/4, t = lane%4) holds rows g and g+8 and the k
-// columns {2t, 2t+1, 2t+8, 2t+9} (+16 for the second step); their (dy, dx, ci) offsets are loop-invariant.
-// Epilogue: scale/shift/leaky, a 4x4 transpose inside each quad so that every thread stores 16 bytes.
+// ---- first conv on tensor cores: 3x3, stride 1, Cin=3 (K = 27 padded to 32), 32 output channels per blockIdx.y ----
+// The layer is HBM-bound (AI ~25 flop/B) and K is only 27, so the A operand (im2col rows) is gathered straight
+// from the L1-cached image into mma.sync m16n8k16 fragments.  One warp walks one image row in 16-pixel tiles:
+// thread (g = lane/4, t = lane%4) holds pixels x0+g and x0+g+8 and the k columns {2t,2t+1,2t+8,2t+9} (+16);
+// their (dy,dx,ci) offsets and the row validity are loop-invariant, x bounds matter only in the first/last tile.
+// The weight columns are permuted (MMA column c of n-tile nt <-> channel (c/2)*8 + 2*nt + c%2) so the four
+// accumulator pairs of a thread are 8 consecutive channels: no shuffles, one 16-byte store per pixel.
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&b);
@@ -148,23 +149,23 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 template <bool U8>
 __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
-                                                             const float* __restrict__ u8_lut, int n_mtiles) {
+                                                             const float* __restrict__ u8_lut, int n_rows) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int c0 = blockIdx.y * 32;
-  const int K = 27;
+  constexpr int K = 27;
+  const int W = in.W, H = in.H;
   // k columns of this thread: j = 0..7 -> k = (j>>2)*16 + ((j>>1)&1)*8 + 2t + (j&1)
-  int koff[8];       // offset (in elements) relative to the output pixel's own input position, or INT_MIN if k >= 27
-  int kdy[8], kdx[8];
+  int koff[8], kdy[8], kdx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
     const int tap = k / 3, ci = k - tap * 3;
-    kdy[j] = (k < K) ? tap / 3 - 1 : 99;
+    kdy[j] = (k < K) ? tap / 3 - 1 : 1000000;      // k >= 27: never valid
     kdx[j] = tap % 3 - 1;
-    koff[j] = (kdy[j] * in.W + kdx[j]) * in.ld + ci;
+    koff[j] = (k < K) ? (kdy[j] * W + kdx[j]) * in.ld + ci : 0;
   }
-  // B fragments: b[ks][nt][0] = {W[ks*16+2t][n], W[ks*16+2t+1][n]}, [1] = rows +8,+9 ; n = c0 + nt*8 + g
+  // B fragments with permuted columns: column g of n-tile nt holds channel c0 + (g/2)*8 + 2*nt + (g&1)
   uint32_t bf[2][4][2];
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
@@ -173,86 +174,69 @@ __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, co
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k = ks * 16 + h * 8 + 2 * t;
-        const int n = c0 + nt * 8 + g;
+        const int n = c0 + (g >> 1) * 8 + 2 * nt + (g & 1);
         const float w0 = (k < K) ? wt[(long long)k * a.cout + n] : 0.0f;
         const float w1 = (k + 1 < K) ? wt[(long long)(k + 1) * a.cout + n] : 0.0f;
         bf[ks][nt][h] = pack_bf16(w0, w1);
       }
-  // epilogue constants of the 8 channels this thread finally stores: c0 + 8t .. c0 + 8t + 7
+  // this thread's 8 output channels: c0 + 8t + j  (accumulator pair of n-tile nt = channels 8t + 2nt, +1)
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = a.scale[c0 + 8 * t + j]; sh[j] = a.shift[c0 + 8 * t + j]; }
 
-  const int hw = in.H * in.W;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int mt = warp_global; mt < n_mtiles; mt += n_warps) {
-    uint32_t afrag[2][4];
-    bool rvalid[2];
+  const int n_xt = (W + 15) >> 4;
+  for (int row = warp_global; row < n_rows; row += n_warps) {       // row = img * H + y
+    const int y = row % H;
+    bool rowok[8];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int m = mt * 16 + g + r * 8;
-      rvalid[r] = m < a.M;
-      const int mm = rvalid[r] ? m : 0;
-      const int img = mm / hw, rem = mm - img * hw;
-      const int y = rem / in.W, x = rem - y * in.W;
-      const long long base = (long long)mm * in.ld;
-      float v[8];
+    for (int j = 0; j < 8; ++j) rowok[j] = (unsigned)(y + kdy[j]) < (unsigned)H;
+    const long long rowbase = (long long)row * W * in.ld;            // element index of pixel (img, y, 0)
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)row * W * a.out_ld + c0 + 8 * t;
+    for (int xt = 0; xt < n_xt; ++xt) {
+      const bool edge = (xt == 0) || (xt * 16 + 17 > W);
+      uint32_t afrag[2][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int yy = y + kdy[j], xx = x + kdx[j];
-        const bool ok = rvalid[r] && yy >= 0 && yy < in.H && xx >= 0 && xx < in.W;
-        float val = 0.0f;
-        if (ok) {
-          if (U8) val = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[base + koff[j]]];
-          else val = __ldg(reinterpret_cast<const float*>(in.ptr) + base + koff[j]);
+      for (int r = 0; r < 2; ++r) {
+        const int x = xt * 16 + g + r * 8;
+        const long long base = rowbase + (long long)x * in.ld;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bool ok = rowok[j];
+          if (edge) ok = ok && (unsigned)(x + kdx[j]) < (unsigned)W && x < W;
+          float val = 0.0f;
+          if (ok) {
+            if (U8) val = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[base + koff[j]]];
+            else val = __ldg(reinterpret_cast<const float*>(in.ptr) + base + koff[j]);
+          }
+          v[j] = val;
         }
-        v[j] = val;
+        afrag[0][r] = pack_bf16(v[0], v[1]);
+        afrag[0][r + 2] = pack_bf16(v[2], v[3]);
+        afrag[1][r] = pack_bf16(v[4], v[5]);
+        afrag[1][r + 2] = pack_bf16(v[6], v[7]);
       }
-      // fragment order: a0:(row g, k 2t..), a1:(row g+8, same), a2:(row g, k +8), a3:(row g+8, k +8)
-      afrag[0][r] = pack_bf16(v[0], v[1]);
-      afrag[0][r + 2] = pack_bf16(v[2], v[3]);
-      afrag[1][r] = pack_bf16(v[4], v[5]);
-      afrag[1][r + 2] = pack_bf16(v[6], v[7]);
-    }
-    float acc[4][4];
+      float acc[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+      for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
-    // acc[nt][0..1] = (row g, channels nt*8 + 2t, +1); acc[nt][2..3] = (row g+8, same channels).
-    // Quad transpose: thread t ends up with n-tile t's eight channels (pairs from lanes 0..3 of the quad).
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float o[8];
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        // lane s sends the pair of n-tile (s + rr) & 3; lane t receives from s = (t - rr) & 3 -> n-tile t
-        const int nts = (t + rr) & 3;
-        float s0 = nts == 0 ? acc[0][2 * r] : nts == 1 ? acc[1][2 * r] : nts == 2 ? acc[2][2 * r] : acc[3][2 * r];
-        float s1 = nts == 0 ? acc[0][2 * r + 1] : nts == 1 ? acc[1][2 * r + 1] : nts == 2 ? acc[2][2 * r + 1] : acc[3][2 * r + 1];
-        const int src = (lane & ~3) | ((t - rr) & 3);
-        s0 = __shfl_sync(0xffffffffu, s0, src);
-        s1 = __shfl_sync(0xffffffffu, s1, src);
-        const int s = (t - rr) & 3;          // the sender's t: its pair covers channels 2s, 2s+1 of the n-tile
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q == s) { o[2 * q] = s0; o[2 * q + 1] = s1; }
-      }
-      if (rvalid[r]) {
+      for (int r = 0; r < 2; ++r) {
+        const int x = xt * 16 + g + r * 8;
         uint32_t pk[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float y0 = o[2 * q] * sc[2 * q] + sh[2 * q];
-          float y1 = o[2 * q + 1] * sc[2 * q + 1] + sh[2 * q + 1];
+        for (int nt = 0; nt < 4; ++nt) {
+          float y0 = acc[nt][2 * r] * sc[2 * nt] + sh[2 * nt];
+          float y1 = acc[nt][2 * r + 1] * sc[2 * nt + 1] + sh[2 * nt + 1];
           if (a.leaky) { y0 = fmaxf(y0, 0.1f * y0); y1 = fmaxf(y1, 0.1f * y1); }
-          pk[q] = pack_bf16(y0, y1);
+          pk[nt] = pack_bf16(y0, y1);
         }
-        const int m = mt * 16 + g + r * 8;
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)m * a.out_ld + c0 + 8 * t;
-        *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (x < W) *reinterpret_cast<uint4*>(orow + (long long)x * a.out_ld) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }

@@ -404,10 +404,10 @@ static int run_op(yb_engine* e, Op& op, int n) {
                           op.out_mode == OUT_PLAIN && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
                           (long long)a.M * op.in.ld < (1ll << 31);
       if (mma_ok) {
-        const int n_mtiles = ceil_div(a.M, 16);
-        dim3 grid(std::min(ceil_div(n_mtiles, 8), e->num_sms * 8), op.cout / 32);
-        if (u8) conv_first_mma_kernel<true><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_mtiles);
-        else conv_first_mma_kernel<false><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_mtiles);
+        const int n_rows = n * op.Ho;      // stride 1: output rows == input rows
+        dim3 grid(std::min(ceil_div(n_rows, 8), e->num_sms * 8), op.cout / 32);
+        if (u8) conv_first_mma_kernel<true><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_rows);
+        else conv_first_mma_kernel<false><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_rows);
         YB_CUDA(cudaGetLastError());
         return YB_OK;
       }
