@@ -147,23 +147,28 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+constexpr int FIRST_ROWS = 8;     // output rows per block (one per warp)
+
 template <bool U8>
 __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
-                                                             const float* __restrict__ u8_lut, int n_rows) {
-  const int lane = threadIdx.x & 31;
+                                                             const float* __restrict__ u8_lut, int n_row_groups) {
+  // Shared memory: FIRST_ROWS + 2 input rows of one image as bf16, each with a one-pixel zero halo left and
+  // right (rows outside the image are zero), so the gather below needs no bounds checks at all.
+  extern __shared__ __align__(16) uint16_t s_in[];
+  const int W = in.W, H = in.H;
+  const int row_elems = (W + 2) * 3 + 2;             // +2: the padded k columns read one element past the halo
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int c0 = blockIdx.y * 32;
   constexpr int K = 27;
-  const int W = in.W, H = in.H;
-  // k columns of this thread: j = 0..7 -> k = (j>>2)*16 + ((j>>1)&1)*8 + 2t + (j&1)
-  int koff[8], kdy[8], kdx[8];
+  // k columns of this thread: j = 0..7 -> k = (j>>2)*16 + ((j>>1)&1)*8 + 2t + (j&1); k = tap*3 + ci
+  int soff[8];          // shared-memory element offset relative to (row = warp, x = 0 incl. halo)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
-    const int tap = k / 3, ci = k - tap * 3;
-    kdy[j] = (k < K) ? tap / 3 - 1 : 1000000;      // k >= 27: never valid
-    kdx[j] = tap % 3 - 1;
-    koff[j] = (k < K) ? (kdy[j] * W + kdx[j]) * in.ld + ci : 0;
+    const int kk = k < K ? k : 0;                    // padded columns read a valid element; their weights are zero
+    const int tap = kk / 3, ci = kk - tap * 3;
+    soff[j] = (tap / 3) * row_elems + (tap % 3) * 3 + ci;
   }
   // B fragments with permuted columns: column g of n-tile nt holds channel c0 + (g/2)*8 + 2*nt + (g&1)
   uint32_t bf[2][4][2];
@@ -179,64 +184,74 @@ __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, co
         const float w1 = (k + 1 < K) ? wt[(long long)(k + 1) * a.cout + n] : 0.0f;
         bf[ks][nt][h] = pack_bf16(w0, w1);
       }
-  // this thread's 8 output channels: c0 + 8t + j  (accumulator pair of n-tile nt = channels 8t + 2nt, +1)
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = a.scale[c0 + 8 * t + j]; sh[j] = a.shift[c0 + 8 * t + j]; }
 
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int groups_per_img = (H + FIRST_ROWS - 1) / FIRST_ROWS;
   const int n_xt = (W + 15) >> 4;
-  for (int row = warp_global; row < n_rows; row += n_warps) {       // row = img * H + y
-    const int y = row % H;
-    bool rowok[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rowok[j] = (unsigned)(y + kdy[j]) < (unsigned)H;
-    const long long rowbase = (long long)row * W * in.ld;            // element index of pixel (img, y, 0)
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)row * W * a.out_ld + c0 + 8 * t;
-    for (int xt = 0; xt < n_xt; ++xt) {
-      const bool edge = (xt == 0) || (xt * 16 + 17 > W);
-      uint32_t afrag[2][4];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int x = xt * 16 + g + r * 8;
-        const long long base = rowbase + (long long)x * in.ld;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          bool ok = rowok[j];
-          if (edge) ok = ok && (unsigned)(x + kdx[j]) < (unsigned)W && x < W;
-          float val = 0.0f;
-          if (ok) {
-            if (U8) val = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[base + koff[j]]];
-            else val = __ldg(reinterpret_cast<const float*>(in.ptr) + base + koff[j]);
-          }
-          v[j] = val;
+  const int row_in = W * 3;                          // input elements per image row (ld == 3)
+  for (int grp = blockIdx.x; grp < n_row_groups; grp += gridDim.x) {
+    const int img = grp / groups_per_img;
+    const int y0 = (grp - img * groups_per_img) * FIRST_ROWS;
+    __syncthreads();                                 // previous group's gathers are done
+    // ---- stage rows y0-1 .. y0+FIRST_ROWS (coalesced), converting to bf16 ----
+    for (int r = 0; r < FIRST_ROWS + 2; ++r) {
+      const int y = y0 - 1 + r;
+      uint16_t* dst = s_in + r * row_elems;
+      const bool inside = (unsigned)y < (unsigned)H;
+      const long long src = ((long long)img * H + y) * row_in;
+      for (int i = threadIdx.x; i < row_elems; i += 256) {
+        const int e = i - 3;                         // element index inside the image row
+        float v = 0.0f;
+        if (inside && e >= 0 && e < row_in) {
+          if (U8) v = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[src + e]];
+          else v = __ldg(reinterpret_cast<const float*>(in.ptr) + src + e);
         }
-        afrag[0][r] = pack_bf16(v[0], v[1]);
-        afrag[0][r + 2] = pack_bf16(v[2], v[3]);
-        afrag[1][r] = pack_bf16(v[4], v[5]);
-        afrag[1][r + 2] = pack_bf16(v[6], v[7]);
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        dst[i] = *reinterpret_cast<uint16_t*>(&b);
       }
-      float acc[4][4];
+    }
+    __syncthreads();
+    const int y = y0 + warp;
+    if (y < H) {
+      const uint16_t* srow = s_in + warp * row_elems;      // smem row `warp` is input row y-1
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)img * H + y) * W * a.out_ld + c0 + 8 * t;
+      for (int xt = 0; xt < n_xt; ++xt) {
+        uint32_t afrag[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+        for (int r = 0; r < 2; ++r) {
+          int x = xt * 16 + g + r * 8;
+          x = x < W ? x : W - 1;                     // tail pixels recompute the last column; they are not stored
+          const uint16_t* p = srow + x * 3;
+          uint32_t v[8];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int x = xt * 16 + g + r * 8;
-        uint32_t pk[4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float y0 = acc[nt][2 * r] * sc[2 * nt] + sh[2 * nt];
-          float y1 = acc[nt][2 * r + 1] * sc[2 * nt + 1] + sh[2 * nt + 1];
-          if (a.leaky) { y0 = fmaxf(y0, 0.1f * y0); y1 = fmaxf(y1, 0.1f * y1); }
-          pk[nt] = pack_bf16(y0, y1);
+          for (int j = 0; j < 8; ++j) v[j] = p[soff[j]];
+          afrag[0][r] = v[0] | (v[1] << 16);
+          afrag[0][r + 2] = v[2] | (v[3] << 16);
+          afrag[1][r] = v[4] | (v[5] << 16);
+          afrag[1][r + 2] = v[6] | (v[7] << 16);
         }
-        if (x < W) *reinterpret_cast<uint4*>(orow + (long long)x * a.out_ld) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int x = xt * 16 + g + r * 8;
+          uint32_t pk[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float y0v = acc[nt][2 * r] * sc[2 * nt] + sh[2 * nt];
+            float y1v = acc[nt][2 * r + 1] * sc[2 * nt + 1] + sh[2 * nt + 1];
+            if (a.leaky) { y0v = fmaxf(y0v, 0.1f * y0v); y1v = fmaxf(y1v, 0.1f * y1v); }
+            pk[nt] = pack_bf16(y0v, y1v);
+          }
+          if (x < W) *reinterpret_cast<uint4*>(orow + (long long)x * a.out_ld) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
   }

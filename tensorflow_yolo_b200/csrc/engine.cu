@@ -402,12 +402,18 @@ static int run_op(yb_engine* e, Op& op, int n) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
       const bool mma_ok = op.ksize == 3 && op.cin == 3 && op.stride == 1 && op.cout % 32 == 0 && !op.out.f32 && !op.has_res &&
                           op.out_mode == OUT_PLAIN && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
-                          (long long)a.M * op.in.ld < (1ll << 31);
+                          op.in.ld == 3 && (FIRST_ROWS + 2) * ((op.in.w + 2) * 3 + 2) * 2 <= 200 * 1024;
       if (mma_ok) {
-        const int n_rows = n * op.Ho;      // stride 1: output rows == input rows
-        dim3 grid(std::min(ceil_div(n_rows, 8), e->num_sms * 8), op.cout / 32);
-        if (u8) conv_first_mma_kernel<true><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_rows);
-        else conv_first_mma_kernel<false><<<grid, 256, 0, st>>>(in, op.d_wt32, a, e->d_u8_lut, n_rows);
+        const int groups = n * ceil_div(op.Ho, FIRST_ROWS);     // stride 1: output rows == input rows
+        const int smem_first = (FIRST_ROWS + 2) * ((op.in.w + 2) * 3 + 2) * 2;
+        dim3 grid(std::min(groups, e->num_sms * 4), op.cout / 32);
+        if (u8) {
+          YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_first));
+          conv_first_mma_kernel<true><<<grid, 256, smem_first, st>>>(in, op.d_wt32, a, e->d_u8_lut, groups);
+        } else {
+          YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_first));
+          conv_first_mma_kernel<false><<<grid, 256, smem_first, st>>>(in, op.d_wt32, a, e->d_u8_lut, groups);
+        }
         YB_CUDA(cudaGetLastError());
         return YB_OK;
       }
