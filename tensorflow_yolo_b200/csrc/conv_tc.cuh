@@ -108,6 +108,19 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_
       "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {   // <= N most recent store groups may still read smem
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -397,16 +410,21 @@ constexpr int CONV_TCP_MAX_COUT_PAD = 1024;
 constexpr int CONV_TCP_HEADER = 1024 + 2 * CONV_TCP_MAX_COUT_PAD * 4;
 constexpr int CONV_TCP_SMEM_MAX = 232448;                             // 227 KB opt-in limit
 constexpr int CONV_TCP_TILE_BUDGET = CONV_TCP_SMEM_MAX - 1024 - CONV_TCP_HEADER;
+// TMA epilogue staging: per epilogue warp two 32-row x 64-byte (SWIZZLE_64B) sub-tiles
+constexpr int CONV_TCP_EPI_BUF = 32 * 64;
+constexpr int CONV_TCP_EPI_BYTES = CONV_TCP_EPI_WARPS * 2 * CONV_TCP_EPI_BUF;
 
 struct PersistArgs {
   int n_tiles_n, n_tiles, cout_pad;
   int n_stages;        // pipeline depth (runtime: fills the shared memory that is left)
   int b_stationary;    // 1: the whole [BN x K] weight matrix is loaded once per CTA and stays in shared memory
+  int tma_epi;         // 1: bf16 plain output through smem + TMA store, residual through TMA load
 };
 
 template <int BN, int BK>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
-conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a,
                        const PersistArgs pa) {
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
@@ -418,13 +436,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tmem_full_bar = empty_bar + CONV_TCP_MAX_STAGES;    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                 // [2]
   uint64_t* b_full_bar = tmem_empty_bar + 2;                    // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_full_bar + 1);
+  uint64_t* res_bar = b_full_bar + 1;                           // [EPI_WARPS][2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * CONV_TCP_EPI_WARPS);
   float* s_scale = reinterpret_cast<float*>(smem + 1024);
   float* s_shift = s_scale + CONV_TCP_MAX_COUT_PAD;
   const int num_k = a.taps * a.kc_blocks;
   const int n_stages = pa.n_stages;
   const bool bstat = pa.b_stationary != 0;
-  uint8_t* b_stat = smem + CONV_TCP_HEADER;                                   // num_k * B_BYTES when stationary
+  uint8_t* epi_smem = smem + CONV_TCP_HEADER;                                 // CONV_TCP_EPI_BYTES when tma_epi
+  uint8_t* b_stat = epi_smem + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);        // num_k * B_BYTES when stationary
   uint8_t* stages = b_stat + (bstat ? num_k * B_BYTES : 0);
   const int stage_bytes = A_BYTES + (bstat ? 0 : B_BYTES);
 
@@ -443,6 +463,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&tmem_empty_bar[s], CONV_TCP_EPI_WARPS);
     }
     mbar_init(b_full_bar, 1);
+    for (int s = 0; s < 2 * CONV_TCP_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+    if (pa.tma_epi) {
+      tma_prefetch_desc(&tmOut);
+      if (a.res != nullptr) tma_prefetch_desc(&tmRes);
+    }
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
@@ -534,6 +559,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int ch_end = (ch_begin + CH_PER < NCH) ? ch_begin + CH_PER : NCH;
     const int hw = a.Ho * a.Wo;
     int it = 0;
+    int epi_idx = 0;            // running sub-tile counter of this warp (selects the staging buffer)
+    uint32_t res_par = 0;       // phase bits of this warp's two residual barriers
     for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -559,6 +586,87 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           opix[0] = ((long long)img * (a.Ho >> 1) + (p >> 1)) * (a.Wo >> 1) + (q >> 1);
           ch_extra = ((p & 1) * 2 + (q & 1)) * a.cout;
         }
+      }
+      if (pa.tma_epi) {
+        // ---------- TMA epilogue: 32 rows x 32 channels per step through swizzled smem ----------
+        const int ew = warp - 2;
+        uint8_t* bufs = epi_smem + ew * 2 * CONV_TCP_EPI_BUF;
+        uint64_t* rbar = res_bar + ew * 2;
+        const int m_warp = tile_m * 128 + quarter * 32;                 // first row of this warp
+        const bool has_res_t = a.res != nullptr;
+        // this lane's row inside the 32x64B sub-tile: 16-byte chunk c lives at chunk (c ^ ((lane >> 1) & 3))
+        const uint32_t row_off = (uint32_t)lane * 64u;
+        const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+        auto issue_res = [&](int chunk, int idx) {                       // lane 0 only
+          const int b = idx & 1;
+          tma_store_wait_read<0>();                                      // the store that last used this buffer has read it
+          mbar_expect_tx(&rbar[b], CONV_TCP_EPI_BUF);
+          tma_load_2d(&tmRes, &rbar[b], bufs + b * CONV_TCP_EPI_BUF, n0 + chunk * 32, m_warp);
+        };
+        if (has_res_t && ch_begin < ch_end && lane == 0) issue_res(ch_begin, epi_idx);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = ch_begin; chunk < ch_end; ++chunk, ++epi_idx) {
+          const int b = epi_idx & 1;
+          uint8_t* buf = bufs + b * CONV_TCP_EPI_BUF;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
+          uint4 rcur[4];
+          if (has_res_t) {
+            if (chunk + 1 < ch_end && lane == 0) issue_res(chunk + 1, epi_idx + 1);
+            mbar_wait(&rbar[b], (res_par >> b) & 1u);
+            res_par ^= (1u << b);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(buf + row_off + (((uint32_t)g ^ sw) << 4));
+          } else {
+            if (lane == 0) tma_store_wait_read<1>();                     // the store two steps ago used this buffer
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          const int cbase = n0 + chunk * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = __uint_as_float(v[j]) * s_scale[cbase + j] + s_shift[cbase + j];
+            if (a.leaky) y = fmaxf(y, 0.1f * y);
+            f[j] = y;
+          }
+          if (has_res_t) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t rw[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&b0);
+            pk.y = *reinterpret_cast<uint32_t*>(&b1);
+            pk.z = *reinterpret_cast<uint32_t*>(&b2);
+            pk.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(buf + row_off + (((uint32_t)g ^ sw) << 4)) = pk;
+          }
+          fence_proxy_async();                 // make the generic-proxy smem writes visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, buf, cbase, m_warp);    // rows >= the tensor's row count and channels >= Cout are clipped
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        continue;
       }
       // residual of the first chunk is requested before waiting for the accumulator
       uint4 rnext[4];
@@ -644,6 +752,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   }
+  if (pa.tma_epi && warp >= 2 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

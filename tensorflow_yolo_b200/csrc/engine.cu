@@ -86,6 +86,20 @@ static int load_driver_fns() {
   return YB_OK;
 }
 
+// generic 2-D bf16 map: [rows, cols] with row pitch ld (elements), box = box_rows x box_cols
+static int make_map_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_rows, int box_cols,
+                       CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%d ld=%d box=%dx%d", (int)r, rows, cols, ld, box_rows, box_cols);
+  return YB_OK;
+}
+
 static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
 
 // [rows, cols] bf16 row-major with row pitch ld (elements); box = box_rows x bk
@@ -246,7 +260,8 @@ struct Op {
   int Ho = 0, Wo = 0, path = PATH_TC, bn_tile = 0, bk = 0, stages = 0;
   __nv_bfloat16* d_wt = nullptr;
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
-  alignas(64) CUtensorMap tmA, tmB;
+  alignas(64) CUtensorMap tmA, tmB, tmOut, tmRes;
+  bool tma_epi = false;
   // generic
   int factor = 0;
 };
@@ -271,6 +286,7 @@ struct yb_engine {
   int bn_max = 128;
   bool persistent = true;
   bool b_stationary = true;
+  bool tma_epilogue = true;
   int num_sms = 148;
   std::vector<Shape> shape;
   std::vector<View> view;
@@ -323,7 +339,7 @@ static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
 }
 
 template <int BN, int BK>
-static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat) {
+static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi) {
   auto kern = conv_tc_persist_kernel<BN, BK>;
   const int a_bytes = 128 * BK * 2, b_bytes = BN * BK * 2;
   const int num_k = a.taps * a.kc_blocks;
@@ -332,25 +348,28 @@ static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int
   pa.n_tiles_n = op.cout_pad / BN;
   pa.n_tiles = tiles_m * pa.n_tiles_n;
   pa.cout_pad = op.cout_pad;
+  pa.tma_epi = (allow_tma_epi && op.tma_epi) ? 1 : 0;
+  const int budget = CONV_TCP_TILE_BUDGET - (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);
   // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
   const long long b_total = (long long)num_k * b_bytes;
-  pa.b_stationary = (allow_bstat && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= CONV_TCP_TILE_BUDGET) ? 1 : 0;
+  pa.b_stationary = (allow_bstat && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= budget) ? 1 : 0;
   const int stage_bytes = a_bytes + (pa.b_stationary ? 0 : b_bytes);
-  const int avail = CONV_TCP_TILE_BUDGET - (pa.b_stationary ? (int)b_total : 0);
+  const int avail = budget - (pa.b_stationary ? (int)b_total : 0);
   pa.n_stages = std::min(CONV_TCP_MAX_STAGES, avail / stage_bytes);
   if (pa.n_stages < 2) return fail(YB_ERR_INVALID, "persistent conv: shared memory too small for BN=%d BK=%d", BN, BK);
-  const int smem = 1024 + CONV_TCP_HEADER + (pa.b_stationary ? (int)b_total : 0) + pa.n_stages * stage_bytes;
+  const int smem = 1024 + CONV_TCP_HEADER + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0) + (pa.b_stationary ? (int)b_total : 0) +
+                   pa.n_stages * stage_bytes;
   YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::min(pa.n_tiles, num_sms);
-  kern<<<grid, CONV_TCP_THREADS, smem, st>>>(op.tmA, op.tmB, a, pa);
+  kern<<<grid, CONV_TCP_THREADS, smem, st>>>(op.tmA, op.tmB, op.tmOut, op.tmRes, a, pa);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
 
-static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat) {
+static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi) {
   if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
 #define YB_CASE(BN_, BK_) \
-  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_>(st, op, a, num_sms, allow_bstat);
+  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_>(st, op, a, num_sms, allow_bstat, allow_tma_epi);
   YB_CASE(256, 64) YB_CASE(128, 64) YB_CASE(64, 64) YB_CASE(32, 64)
   YB_CASE(128, 32) YB_CASE(64, 32) YB_CASE(32, 32)
 #undef YB_CASE
@@ -396,7 +415,7 @@ static int run_op(yb_engine* e, Op& op, int n) {
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary));
+      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary, e->tma_epilogue));
       else YB_TRY(dispatch_conv_tc(st, op, a));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
@@ -714,6 +733,16 @@ static int build_tensor_maps(yb_engine* e) {
     }
     const int K = op.ksize * op.ksize * op.cin;
     YB_TRY(make_tiled_map(&op.tmB, op.d_wt, op.cout_pad, K, K, op.bn_tile, op.bk));
+    // TMA epilogue (plain bf16 outputs): 32 rows x 32 channels per store, 64-byte swizzle
+    op.tma_epi = false;
+    memset(&op.tmOut, 0, sizeof(op.tmOut));
+    memset(&op.tmRes, 0, sizeof(op.tmRes));
+    if (op.out_mode == OUT_PLAIN && !op.out.f32) {
+      const long long rows = (long long)e->max_batch * op.Ho * op.Wo;
+      YB_TRY(make_map_2d(&op.tmOut, view_ptr(e, op.out), rows, op.cout, op.out.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+      if (op.has_res) YB_TRY(make_map_2d(&op.tmRes, view_ptr(e, op.in2), rows, op.cout, op.in2.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+      op.tma_epi = true;
+    }
   }
   return YB_OK;
 }
@@ -784,6 +813,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   const char* ps = getenv("YB_PERSIST");
   if (ps) e->persistent = atoi(ps) != 0;
   if (e->persistent) e->bn_max = 256;
+  const char* te = getenv("YB_TMA_EPI");
+  if (te) e->tma_epilogue = atoi(te) != 0;
   const char* bs = getenv("YB_BSTAT");
   if (bs) e->b_stationary = atoi(bs) != 0;
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
