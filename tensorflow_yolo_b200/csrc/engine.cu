@@ -348,7 +348,9 @@ static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int
   pa.n_tiles_n = op.cout_pad / BN;
   pa.n_tiles = tiles_m * pa.n_tiles_n;
   pa.cout_pad = op.cout_pad;
-  pa.tma_epi = (allow_tma_epi && op.tma_epi) ? 1 : 0;
+  // The staging buffers cost one pipeline stage at BN=256: worth it while the epilogue is the long pole
+  // (K <= 1152), not for the K-heavy 26x26/13x13 layers whose epilogue already hides behind the MMAs.
+  pa.tma_epi = (allow_tma_epi && op.tma_epi && (BN < 256 || num_k * BK <= 1152)) ? 1 : 0;
   const int budget = CONV_TCP_TILE_BUDGET - (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);
   // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
   const long long b_total = (long long)num_k * b_bytes;
