@@ -111,7 +111,7 @@ def run_reference(args):
     """--impl reference: the CPU implementation of the path (oracle port; TensorFlow is not installable, the
     reference's decode/NMS are restated in vectorised numpy) on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
-        return
+        return None
     from tensorflow_yolo_b200 import synth
     sample = args.cpu_images
     topo, stream, geo, threads = cpu_setup(args.size)
@@ -124,14 +124,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     what = "{} image(s) per step of the same synthetic 416 workload".format(sample)
-    print(json.dumps({
+    return ({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "YOLOv3-{} COCO-80 conv stack + decode + NMS, CPU oracle port".format(args.size),
                    "images_per_step": sample, "threshold": THRESHOLD, "iou_threshold": IOU_THRESHOLD},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": what},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def run_ours(args):
@@ -230,7 +230,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
     # ---- roofline of the dominant kernel: the tcgen05 conv launch class with the largest share of the step ----
     classes, conv_ms, conv_flops, other_ms = {}, 0.0, 0.0, 0.0
@@ -307,9 +307,9 @@ def run_ours(args):
         "gpu_launches": world * K * (fwd_l + det_l), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "conv_gflop_per_image": flops_img / 1e9,
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -326,10 +326,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default=None, help="write the per-op CUDA-event table of the timed region (JSON)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: anything a library prints meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
