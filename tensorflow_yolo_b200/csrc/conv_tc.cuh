@@ -121,6 +121,73 @@ __device__ __forceinline__ void tma_store_wait_read() {   // <= N most recent st
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- 2-CTA (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier of the pair's leader CTA (cluster address `mbar`)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t mbar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(const CUtensorMap* m, uint32_t mbar, void* dst, int c, int w, int h,
+                                                        int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs] * B[smem of both CTAs]: M = 256 (128 rows per CTA), issued by the leader
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in every CTA of `mask` once the leader's prior MMAs are complete
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+template <int BN, int M>
+__device__ __forceinline__ constexpr uint32_t make_idesc_m() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -421,14 +488,21 @@ struct PersistArgs {
   int tma_epi;         // 1: bf16 plain output through smem + TMA store, residual through TMA load
 };
 
-template <int BN, int BK>
+// PAIR = true: launched as 2-CTA clusters.  The pair computes a 256(M) x 256(N) tile with tcgen05.mma.cta_group::2:
+// CTA r holds the A rows of M tile 2j+r and the B rows [128r, 128r+128) of the N tile, so every SM ingests 32 KB
+// per K step instead of 48 KB; the leader (rank 0) issues the MMAs, both CTAs' TMA loads complete on the leader's
+// full barriers, the leader's commits release the smem stages / publish the accumulators in both CTAs, and both
+// CTAs' epilogue warps hand the accumulator back on the leader's tmem_empty barrier.
+template <int BN, int BK, bool PAIR>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a,
                        const PersistArgs pa) {
+  static_assert(!PAIR || BN == 256, "the CTA pair computes 256 x 256 tiles");
   constexpr int A_BYTES = 128 * BK * 2;
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;      // bytes of B this CTA loads per K step
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
@@ -455,12 +529,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], PAIR ? 2 : 1);            // pair: both producers arrive on the leader's barrier
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], CONV_TCP_EPI_WARPS);
+      mbar_init(&tmem_empty_bar[s], (PAIR ? 2 : 1) * CONV_TCP_EPI_WARPS);
     }
     mbar_init(b_full_bar, 1);
     for (int s = 0; s < 2 * CONV_TCP_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
@@ -469,17 +543,23 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (a.res != nullptr) tma_prefetch_desc(&tmRes);
     }
     fence_barrier_init();
-  } else if (warp == 1) {
-    tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  }
+  if (PAIR) cluster_sync_all();                        // peer barriers are initialised before anything remote arrives
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_ptr_smem);
+    else tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   }
   for (int i = threadIdx.x; i < pa.cout_pad; i += CONV_TCP_THREADS) {
     s_scale[i] = a.scale[i];
     s_shift[i] = a.shift[i];
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // tile walk: single CTA -> tiles blockIdx.x, +gridDim.x, ...; pair -> pair-tiles (cluster id), M tile = 2j + rank
+  const int walk_start = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walk_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -491,9 +571,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       const int hw = a.Ho * a.Wo;
-      for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x) {
-        const int tile_m = tile / pa.n_tiles_n;
-        const int n0 = (tile - tile_m * pa.n_tiles_n) * BN;
+      const uint32_t full0 = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;       // leader's full_bar[0]
+      for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step) {
+        const int tile_mj = tile / pa.n_tiles_n;
+        const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
+        const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;
         const int m0 = tile_m * 128;
         int img = 0, base_w = 0, base_h = 0;
         if (a.im2col) {
@@ -507,18 +589,27 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stages + stage * stage_bytes;
+          if (PAIR) {
+            const uint32_t fb = full0 + (uint32_t)stage * 8u;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);   // bytes of both CTAs
+            else mbar_arrive_cluster(fb);
+            if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+            else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
+            tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
+          } else {
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
           else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
           if (!bstat) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+          }
           if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    constexpr uint32_t idesc = make_idesc<BN>();
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------ MMA issuer (pair: leader CTA only) ------------------------------
+    constexpr uint32_t idesc = PAIR ? make_idesc_m<BN, 256>() : make_idesc<BN>();
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -527,7 +618,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_after();
     }
     const uint32_t b_stat_addr = smem_u32(b_stat);
-    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
@@ -540,19 +631,27 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t sa = smem_u32(stages + stage * stage_bytes);
           const uint64_t da = make_kmajor_desc<BK>(sa);
           const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)(kb * B_BYTES) : sa + A_BYTES);
+          if (PAIR) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (kb == num_k - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;                 // 0 or 1
+    const uint32_t tmem_empty0 = PAIR ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0u;   // leader's tmem_empty_bar[0]
     constexpr int NCH = BN / 32;                      // 32-column chunks per tile
     constexpr int CH_PER = (NCH + 1) / 2;
     const int ch_begin = half * CH_PER;
@@ -561,11 +660,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int it = 0;
     int epi_idx = 0;            // running sub-tile counter of this warp (selects the staging buffer)
     uint32_t res_par = 0;       // phase bits of this warp's two residual barriers
-    for (int tile = blockIdx.x; tile < pa.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int tile_m = tile / pa.n_tiles_n;
-      const int n0 = (tile - tile_m * pa.n_tiles_n) * BN;
+      const int tile_mj = tile / pa.n_tiles_n;
+      const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
+      const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;
       const int m = tile_m * 128 + quarter * 32 + lane;
       const bool valid = m < a.M;
       long long opix[4];
@@ -665,7 +765,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        }
         continue;
       }
       // residual of the first chunk is requested before waiting for the accumulator
@@ -748,16 +851,18 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
       }
     }
   }
   if (pa.tma_epi && warp >= 2 && lane == 0) tma_store_wait_all();
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: nobody exits while the peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 

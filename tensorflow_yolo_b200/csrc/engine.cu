@@ -260,7 +260,7 @@ struct Op {
   int Ho = 0, Wo = 0, path = PATH_TC, bn_tile = 0, bk = 0, stages = 0;
   __nv_bfloat16* d_wt = nullptr;
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
-  alignas(64) CUtensorMap tmA, tmB, tmOut, tmRes;
+  alignas(64) CUtensorMap tmA, tmB, tmOut, tmRes, tmBh;   // tmBh: half-N box for the CTA-pair kernel
   bool tma_epi = false;
   // generic
   int factor = 0;
@@ -287,6 +287,7 @@ struct yb_engine {
   bool persistent = true;
   bool b_stationary = true;
   bool tma_epilogue = true;
+  bool cta_pairs = true;
   int num_sms = 148;
   std::vector<Shape> shape;
   std::vector<View> view;
@@ -338,19 +339,20 @@ static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
   return YB_OK;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool PAIR>
 static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi) {
-  auto kern = conv_tc_persist_kernel<BN, BK>;
-  const int a_bytes = 128 * BK * 2, b_bytes = BN * BK * 2;
+  auto kern = conv_tc_persist_kernel<BN, BK, PAIR>;
+  const int a_bytes = 128 * BK * 2, b_bytes = (PAIR ? BN / 2 : BN) * BK * 2;
   const int num_k = a.taps * a.kc_blocks;
   PersistArgs pa;
-  const int tiles_m = ceil_div(a.M, 128);
+  const int tiles_m = PAIR ? ceil_div(ceil_div(a.M, 128), 2) : ceil_div(a.M, 128);    // pair: pairs of M tiles
+  if (PAIR) allow_bstat = false;
   pa.n_tiles_n = op.cout_pad / BN;
   pa.n_tiles = tiles_m * pa.n_tiles_n;
   pa.cout_pad = op.cout_pad;
   // The staging buffers cost one pipeline stage at BN=256: worth it while the epilogue is the long pole
   // (K <= 1152), not for the K-heavy 26x26/13x13 layers whose epilogue already hides behind the MMAs.
-  pa.tma_epi = (allow_tma_epi && op.tma_epi && (BN < 256 || num_k * BK <= 1152)) ? 1 : 0;
+  pa.tma_epi = (allow_tma_epi && op.tma_epi && (BN < 256 || PAIR || num_k * BK <= 1152)) ? 1 : 0;
   const int budget = CONV_TCP_TILE_BUDGET - (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);
   // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
   const long long b_total = (long long)num_k * b_bytes;
@@ -362,16 +364,35 @@ static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int
   const int smem = 1024 + CONV_TCP_HEADER + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0) + (pa.b_stationary ? (int)b_total : 0) +
                    pa.n_stages * stage_bytes;
   YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (PAIR) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const int clusters = std::min(pa.n_tiles, num_sms / 2);
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(CONV_TCP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    YB_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmBh, op.tmOut, op.tmRes, a, pa));
+    return YB_OK;
+  }
   const int grid = std::min(pa.n_tiles, num_sms);
   kern<<<grid, CONV_TCP_THREADS, smem, st>>>(op.tmA, op.tmB, op.tmOut, op.tmRes, a, pa);
   YB_CUDA(cudaGetLastError());
   return YB_OK;
 }
 
-static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi) {
+static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi,
+                             bool allow_pair) {
   if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
+  // CTA pairs (cta_group::2) for the operand-bandwidth-bound layers: N tile 256, K >= 512
+  if (allow_pair && op.bn_tile == 256 && op.bk == 64 && a.taps * a.kc_blocks * 64 >= 512 && ceil_div(a.M, 128) >= 2)
+    return launch_conv_tcp<256, 64, true>(st, op, a, num_sms, false, allow_tma_epi);
 #define YB_CASE(BN_, BK_) \
-  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_>(st, op, a, num_sms, allow_bstat, allow_tma_epi);
+  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, false>(st, op, a, num_sms, allow_bstat, allow_tma_epi);
   YB_CASE(256, 64) YB_CASE(128, 64) YB_CASE(64, 64) YB_CASE(32, 64)
   YB_CASE(128, 32) YB_CASE(64, 32) YB_CASE(32, 32)
 #undef YB_CASE
@@ -417,7 +438,7 @@ static int run_op(yb_engine* e, Op& op, int n) {
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary, e->tma_epilogue));
+      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary, e->tma_epilogue, e->cta_pairs));
       else YB_TRY(dispatch_conv_tc(st, op, a));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
@@ -735,6 +756,8 @@ static int build_tensor_maps(yb_engine* e) {
     }
     const int K = op.ksize * op.ksize * op.cin;
     YB_TRY(make_tiled_map(&op.tmB, op.d_wt, op.cout_pad, K, K, op.bn_tile, op.bk));
+    memset(&op.tmBh, 0, sizeof(op.tmBh));
+    if (op.bn_tile == 256 && op.bk == 64) YB_TRY(make_tiled_map(&op.tmBh, op.d_wt, op.cout_pad, K, K, 128, op.bk));
     // TMA epilogue (plain bf16 outputs): 32 rows x 32 channels per store, 64-byte swizzle
     op.tma_epi = false;
     memset(&op.tmOut, 0, sizeof(op.tmOut));
@@ -815,6 +838,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   const char* ps = getenv("YB_PERSIST");
   if (ps) e->persistent = atoi(ps) != 0;
   if (e->persistent) e->bn_max = 256;
+  const char* cp = getenv("YB_PAIR");
+  if (cp) e->cta_pairs = atoi(cp) != 0;
   const char* te = getenv("YB_TMA_EPI");
   if (te) e->tma_epilogue = atoi(te) != 0;
   const char* bs = getenv("YB_BSTAT");
