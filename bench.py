@@ -101,6 +101,11 @@ def cpu_pipeline(topo, stream, geo, images):
 def cpu_setup(size):
     import torch
     from oracle import convstack
+    # all host threads the process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(os.cpu_count() or 1)
     net, state, stream, shape = build_network(size)
     topo = convstack.topology_v3(NUM_CLASSES, np.reshape(V3_ANCHORS, [-1, 2]), shape)
     geo = convstack.yolo_geometry(topo, shape)
@@ -165,6 +170,12 @@ def run_ours(args):
     eng = yb.Engine(state.plan(), shape, NUM_CLASSES, yb.YB_DECODE_V3, max_batch=B, device=local)
     eng.load_weights(stream)
     flops_img = yplan.conv_flops(state.graph.specs)
+    tune = None
+    if not args.no_autotune:
+        tune = eng.autotune(B, reps=5)          # one-off, outside every timed region
+        if args.dump_tune and rank == 0:
+            with open(args.dump_tune, "w") as f:
+                json.dump(tune, f, indent=0)
 
     g = torch.Generator(device="cuda"); g.manual_seed(1 + rank)
     x_dev = torch.rand((B,) + shape, device="cuda", dtype=torch.float32, generator=g)      # resident in HBM
@@ -189,7 +200,6 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     # ---- timed region 1: inputs resident in HBM, device events on the engine's stream ----
-    eng.profiling(True)
     barrier()
     eng.mark(0)
     for _ in range(K):
@@ -198,9 +208,21 @@ def run_ours(args):
     eng.sync()
     barrier()
     ms = max_over_ranks(eng.elapsed_ms(0, 1))
+    value = world * B * K / (ms * 1e-3)
+    # ---- the same K steps again with a CUDA event between launches: per-kernel times for the roofline.  (Kept out
+    # of region 1 because an event between two launches serialises them, i.e. switches off the programmatic dependent
+    # launch overlap the step normally runs with.) ----
+    eng.profiling(True)
+    barrier()
+    eng.mark(2)
+    for _ in range(K):
+        step_device()
+    eng.mark(3)
+    eng.sync()
+    barrier()
+    ms_prof = eng.elapsed_ms(2, 3)
     prof, n_fwd = eng.profile_read()
     eng.profiling(False)
-    value = world * B * K / (ms * 1e-3)
 
     # ---- timed region 2: end to end through host buffers (H2D of uint8 images + D2H of detections each step) ----
     def e2e_loop(steps):
@@ -238,7 +260,8 @@ def run_ours(args):
         info = eng.op_info(op_i)
         if info["path"] == 0:
             spec = state.graph.specs[layer]
-            key = (spec.shape, spec.ksize, spec.stride, state.graph.specs[spec.src[0]].shape[2], info["bn"], info["bk"], info["stages"])
+            cfg = eng.op_cfg(op_i)
+            key = (spec.shape, spec.ksize, spec.stride, state.graph.specs[spec.src[0]].shape[2], info["bn"], info["bk"], cfg["pair"])
             c = classes.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
             c["ms"] += ms_sum; c["flops"] += info["flops_per_image"] * B * n_fwd; c["launches"] += n_fwd
             conv_ms += ms_sum; conv_flops += info["flops_per_image"] * B * n_fwd
@@ -251,12 +274,14 @@ def run_ours(args):
             spec = state.graph.specs[layer]
             fl = info["flops_per_image"] * B
             t = ms_sum / max(n_fwd, 1)
+            cfg = eng.op_cfg(op_i)
             rows.append({"op": op_i, "layer": layer, "kind": yplan.KIND_NAMES[spec.kind], "out_hwc": list(spec.shape),
                          "ksize": spec.ksize, "stride": spec.stride, "cin": state.graph.specs[spec.src[0]].shape[2] if spec.src else 0,
                          "path": info["path"], "bn": info["bn"], "bk": info["bk"], "stages": info["stages"],
+                         "pair": cfg["pair"], "bstat": cfg["bstat"], "tma_epi": cfg["tma_epi"],
                          "ms": t, "tflops": (fl / (t * 1e-3) / 1e12) if t > 0 and fl > 0 else 0.0})
         with open(args.dump_profile, "w") as f:
-            json.dump({"batch": B, "forwards": n_fwd, "step_ms": ms / K, "ops": rows}, f, indent=0)
+            json.dump({"batch": B, "forwards": n_fwd, "step_ms": ms / K, "step_ms_with_events": ms_prof / K, "ops": rows}, f, indent=0)
     top_key, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
     achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
@@ -265,12 +290,14 @@ def run_ours(args):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    (ho, wo, co), ks, st, cin, bn, bk, stg = top_key
+    (ho, wo, co), ks, st, cin, bn, bk, pair = top_key
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": "{} bf16_tflops_sustained (kernel timed inside a long step)".format(peaks["source"]),
-        "kernel": "conv_tc_kernel<BN={},BK={},STAGES={}>: {}x{} s{} conv {}->{} @{}x{} (share of step {:.1%}, {} launches/step)".format(
-            bn, bk, stg, ks, ks, st, cin, co, ho, wo, top["ms"] / (ms * n_fwd / K if n_fwd else 1), top["launches"] // max(n_fwd, 1)),
+        "kernel": "conv_tc_persist_kernel<BN={},BK={},PAIR={}>: {}x{} s{} conv {}->{} @{}x{} (share of step {:.1%}, {} launches/step)".format(
+            bn, bk, pair, ks, ks, st, cin, co, ho, wo, top["ms"] / (ms_prof * n_fwd / K if n_fwd else 1), top["launches"] // max(n_fwd, 1)),
+        "timing": "CUDA events between launches on the engine's stream over K steps repeated right after the timed region "
+                  "({:.3f} ms/step with the events, {:.3f} without)".format(ms_prof / K, ms / K),
         "conv_stack": {"achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12, "frac_of_sustained": conv_flops / (conv_ms * 1e-3) / 1e12 / peak,
                        "frac_of_burst": conv_flops / (conv_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
                        "ms_per_step": conv_ms / max(n_fwd, 1), "other_forward_ms_per_step": other_ms / max(n_fwd, 1)},
@@ -303,9 +330,13 @@ def run_ours(args):
                        B * shape[0] * shape[1] * 3 * 4 // 2 ** 20),
                    "kept_detections_per_image": kept / float(B * K)},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * B * shape[0] * shape[1] * 3,
-                "d2h_bytes_per_step": world * B * (cap * 40 + 4), "input": "uint8 NHWC in pinned host memory, scaled by 1/255 on the device"},
+                "d2h_bytes_per_step": world * B * (cap * 40 + 4), "input": "uint8 NHWC in pinned host memory, scaled by 1/255 on the device",
+                "timer": "host wall clock around the synchronised region, max over ranks"},
         "gpu_launches": world * K * (fwd_l + det_l), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "conv_gflop_per_image": flops_img / 1e9,
+        "autotune": None if tune is None else {
+            "layers_changed": sum(1 for o in tune["ops"] if o["chosen"]["ms"] < o["default_ms"] * 0.985),
+            "classes": len(tune["ops"])},
     }
     if world > 1:
         dist.destroy_process_group()
@@ -325,6 +356,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-clock budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default=None, help="write the per-op CUDA-event table of the timed region (JSON)")
+    ap.add_argument("--no-autotune", action="store_true", help="keep the heuristic conv launch configurations")
+    ap.add_argument("--dump-tune", default=None, help="write the autotuner's candidate table (JSON)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library prints meanwhile (e.g. NCCL's version banner) goes to stderr
     sys.stdout.flush()

@@ -145,6 +145,21 @@ int yb_engine_profile(yb_engine* e, const void* images, int dtype, int mem, int 
 /* conv implementation: 0 = tcgen05/TMA implicit GEMM (default), 1 = plain CUDA-core kernel
  * (debug cross-check only; never selected implicitly). */
 int yb_engine_set_conv_impl(yb_engine* e, int impl);
+/* Measures, on the device, every launch configuration of each tcgen05 conv (N tile 32..256, cta_group::2 CTA pairs,
+ * weight-stationary B, TMA-store epilogue) for a batch of n images and keeps the fastest per layer; layers with the
+ * same shape share one measurement.  Results do not change (the K reduction order is the same in every
+ * configuration).  Clobbers the activations: call yb_engine_forward again before reading outputs.  reps <= 0 = 5. */
+int yb_engine_autotune(yb_engine* e, int n, int reps);
+/* JSON written by the last yb_engine_autotune (every candidate with its time).  buf may be NULL to query *needed. */
+int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* needed);
+/* Debug / measurement switches: "pdl" (programmatic dependent launch between convs, default 1), "pairs", "bstat",
+ * "tma_epi" (allow those kernel features, default 1), "ablate" (bit mask of roofline probes of the conv kernel:
+ * 1 = no epilogue work, 2 = no MMAs, 4 = no activation loads, 8 = no weight loads; outputs are wrong while set). */
+int yb_engine_set_option(yb_engine* e, const char* name, int value);
+/* Forces the launch configuration of launched op `op_index` (bn = 0 restores the heuristic; bstat / tma_epi: -1 =
+ * heuristic, 0 = off, 1 = on when possible) and times one op in isolation (average of reps launches, milliseconds). */
+int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi);
+int yb_engine_time_op(yb_engine* e, int op_index, int n, int reps, float* ms);
 /* number of kernel launches the last forward / detect enqueued */
 int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches);
 
@@ -167,6 +182,10 @@ int yb_engine_profile_read(yb_engine* e, int* layer_idx, float* ms_sum, int cap,
  * negative = non-conv kernel; tile shape; algorithmic FLOPs per image (2*MAC). */
 int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn_tile, int* bk, int* stages,
                       double* flops_per_image);
+
+/* Launch configuration of op `op_index` as resolved by its last launch: N tile, CTA pairs, weight-stationary B,
+ * TMA-store epilogue, pipeline stages. */
+int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages);
 
 /* ---- stand-alone post-processing on caller tensors ---- */
 typedef struct yb_scale {

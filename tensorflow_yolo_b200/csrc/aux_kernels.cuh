@@ -389,4 +389,13 @@ __global__ void read_view_kernel(const void* in, int ld, int C, int is_f32, floa
                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[pix * ld + c]);
 }
 
+// pseudo-random bytes (autotuner input images)
+__global__ void fill_u8_hash_kernel(unsigned char* out, long long total, unsigned seed) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  unsigned x = (unsigned)gid * 2654435761u + seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  out[gid] = (unsigned char)(x & 0xFFu);
+}
+
 }  // namespace yb

@@ -120,6 +120,11 @@ __device__ __forceinline__ void tma_store_wait_read() {   // <= N most recent st
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Programmatic dependent launch: the next kernel in the stream may start its prologue (barrier init, TMEM
+// allocation, weight loads) once every CTA of this grid has passed launch_dependents; it must not touch anything the
+// previous grids wrote (or still read) before griddep_wait() returns.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- 2-CTA (cta_group::2) helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -249,219 +254,8 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int BN, int BK, int STAGES>
-struct ConvTcSmem {
-  static constexpr int A_BYTES = 128 * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  // full[STAGES], empty[STAGES], tmem_full, tmem ptr, then scale/shift staging
-  static constexpr int SS_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8;
-  static constexpr int TOTAL = SS_OFFSET + 2 * BN * 4 + 1024;  // + slack for manual 1024B alignment
-};
-
-constexpr int CONV_TC_THREADS = 192;  // warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps 2-5 epilogue
-
-template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(CONV_TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
-               const int n_tiles_n) {
-  using L = ConvTcSmem<BN, BK, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(smem + L::SS_OFFSET);
-  float* s_shift = s_scale + BN;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % n_tiles_n;
-  const int tile_m = blockIdx.x / n_tiles_n;
-  const int m0 = tile_m * 128;
-  const int n0 = tile_n * BN;
-  const int num_k = a.taps * a.kc_blocks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  } else if (warp == 1) {
-    tmem_alloc<BN>(tmem_ptr_smem);
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      s_scale[i] = a.scale[n0 + i];
-      s_shift[i] = a.shift[n0 + i];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (elect_one()) {
-      int img = 0, p0 = 0, q0 = 0;
-      if (a.im2col) {
-        const int hw = a.Ho * a.Wo;
-        img = m0 / hw;
-        const int rem = m0 - img * hw;
-        p0 = rem / a.Wo;
-        q0 = rem - p0 * a.Wo;
-      }
-      const int base_w = q0 * a.conv_stride - a.pad;
-      const int base_h = p0 * a.conv_stride - a.pad;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        const int tap = kb / a.kc_blocks;
-        const int cb = kb - tap * a.kc_blocks;
-        if (a.im2col) {
-          const int kh = tap / a.ksize;
-          const int kw = tap - kh * a.ksize;
-          tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-        } else {
-          tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
-        }
-        tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    constexpr uint32_t idesc = make_idesc<BN>();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < num_k; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint64_t da = make_kmajor_desc<BK>(sa);
-        const uint64_t db = make_kmajor_desc<BK>(sa + L::A_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[stage]);                   // frees this smem stage when the MMAs retire
-        if (kb == num_k - 1) umma_commit(tmem_full_bar);  // accumulator complete
-      }
-      __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-  } else {
-    // ------------------------------ epilogue (4 warps, one TMEM lane quarter each) ------------------------------
-    const int quarter = warp & 3;
-    const int m = m0 + quarter * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool valid = m < a.M;
-    // destination pixel(s)
-    long long opix[4];
-    int n_dst = 1;
-    int ch_extra = 0;
-    if (a.out_mode == OUT_PLAIN) {
-      opix[0] = m;
-    } else {
-      const int hw = a.Ho * a.Wo;
-      const int img = m / hw;
-      const int rem = m - img * hw;
-      const int p = rem / a.Wo;
-      const int q = rem - p * a.Wo;
-      if (a.out_mode == OUT_UPSAMPLE2) {
-        const long long W2 = 2 * a.Wo;
-        const long long base = ((long long)img * 2 * a.Ho + 2 * p) * W2 + 2 * q;
-        opix[0] = base; opix[1] = base + 1; opix[2] = base + W2; opix[3] = base + W2 + 1;
-        n_dst = 4;
-      } else {  // OUT_REORG2: out[n, p/2, q/2, ((p%2)*2 + q%2)*cout + c]
-        opix[0] = ((long long)img * (a.Ho >> 1) + (p >> 1)) * (a.Wo >> 1) + (q >> 1);
-        ch_extra = ((p & 1) * 2 + (q & 1)) * a.cout;
-      }
-    }
-#pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chunk * 32), v);
-      tmem_ld_wait();
-      const int cbase = n0 + chunk * 32;  // first output channel of this chunk
-      if (valid && cbase < a.cout) {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = __uint_as_float(v[j]) * s_scale[chunk * 32 + j] + s_shift[chunk * 32 + j];
-          if (a.leaky) y = fmaxf(y, 0.1f * y);
-          f[j] = y;
-        }
-        if (a.res != nullptr) {
-          const __nv_bfloat16* rp = a.res + (long long)m * a.res_ld + cbase;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (cbase + g * 8 < a.cout) {
-              const uint4 r = *reinterpret_cast<const uint4*>(rp + g * 8);
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
-                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
-              }
-            }
-          }
-        }
-        if (a.out_f32) {
-          float* op = reinterpret_cast<float*>(a.out) + opix[0] * a.out_ld + cbase;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (cbase + g * 4 < a.out_ld)  // head buffers are padded to a multiple of 4 channels
-              *reinterpret_cast<float4*>(op + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-          }
-        } else {
-          uint4 pk[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
-            __nv_bfloat162 b1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
-            __nv_bfloat162 b3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
-            pk[g].x = *reinterpret_cast<uint32_t*>(&b0);
-            pk[g].y = *reinterpret_cast<uint32_t*>(&b1);
-            pk[g].z = *reinterpret_cast<uint32_t*>(&b2);
-            pk[g].w = *reinterpret_cast<uint32_t*>(&b3);
-          }
-          for (int d = 0; d < n_dst; ++d) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + opix[d] * a.out_ld + ch_extra + cbase;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (cbase + g * 8 < a.cout) *reinterpret_cast<uint4*>(op + g * 8) = pk[g];
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
-  }
-}
-
 // ================================================================================================
-// Persistent variant: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers let the
+// Persistent kernel: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers let the
 // epilogue of tile i (TMEM -> registers -> global) overlap the mainloop of tile i+1, the TMA producer
 // runs ahead across tile boundaries, and the per-CTA fixed costs (TMEM alloc, barrier init, descriptor
 // prefetch, scale/shift staging) are paid once per SM instead of once per tile.
@@ -486,6 +280,8 @@ struct PersistArgs {
   int n_stages;        // pipeline depth (runtime: fills the shared memory that is left)
   int b_stationary;    // 1: the whole [BN x K] weight matrix is loaded once per CTA and stays in shared memory
   int tma_epi;         // 1: bf16 plain output through smem + TMA store, residual through TMA load
+  int ablate;          // debug/roofline probes (results are wrong when non-zero): 1 = epilogue does nothing,
+                       // 2 = no MMAs, 4 = no A loads, 8 = no B loads
 };
 
 // PAIR = true: launched as 2-CTA clusters.  The pair computes a 256(M) x 256(N) tile with tcgen05.mma.cta_group::2:
@@ -524,6 +320,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -564,10 +361,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      if (bstat) {
+      if (bstat) {      // weights do not depend on the previous kernel: fetched before the grid dependency resolves
         mbar_expect_tx(b_full_bar, (uint32_t)(num_k * B_BYTES));
         for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, b_full_bar, b_stat + kb * B_BYTES, kb * BK, 0);
       }
+      griddep_wait();
+      const bool load_a = !(pa.ablate & 4), load_b = !bstat && !(pa.ablate & 8);
+      const uint32_t tx_bytes = (load_a ? (uint32_t)A_BYTES : 0u) + (load_b ? (uint32_t)B_BYTES : 0u);
       int stage = 0;
       uint32_t phase = 0;
       const int hw = a.Ho * a.Wo;
@@ -591,16 +391,20 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint8_t* sa = stages + stage * stage_bytes;
           if (PAIR) {
             const uint32_t fb = full0 + (uint32_t)stage * 8u;
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);   // bytes of both CTAs
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes);   // bytes of both CTAs
             else mbar_arrive_cluster(fb);
-            if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-            else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
-            tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
+            if (load_a) {
+              if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+              else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
+            }
+            if (load_b) tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
           } else {
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-          else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
-          if (!bstat) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (load_a) {
+              if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+              else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+            }
+            if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
           }
           if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -631,16 +435,21 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t sa = smem_u32(stages + stage * stage_bytes);
           const uint64_t da = make_kmajor_desc<BK>(sa);
           const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)(kb * B_BYTES) : sa + A_BYTES);
+          const bool do_mma = !(pa.ablate & 2);
           if (PAIR) {
+            if (do_mma) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_pair(&empty_bar[stage], 3);
             if (kb == num_k - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
           } else {
+            if (do_mma) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
           }
         }
         __syncwarp();
@@ -660,9 +469,21 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int it = 0;
     int epi_idx = 0;            // running sub-tile counter of this warp (selects the staging buffer)
     uint32_t res_par = 0;       // phase bits of this warp's two residual barriers
+    griddep_wait();             // residual reads and output stores must follow the previous kernels
     for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      if (pa.ablate & 1) {      // probe: accumulator handed straight back
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        }
+        continue;
+      }
       const int tile_mj = tile / pa.n_tiles_n;
       const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
       const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;

@@ -252,15 +252,28 @@ struct Buf {
 enum OpKind { OP_CONV = 0, OP_MAXPOOL, OP_ADD, OP_UPSAMPLE, OP_REORG, OP_COPY };
 enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2 };
 
+// How one tcgen05 conv is launched.  compile_plan fills in a heuristic; yb_engine_autotune replaces it with the
+// fastest measured candidate.
+struct ConvCfg {
+  int bn = 0;          // N tile (TMEM columns per accumulator): 32, 64, 128 or 256
+  int pair = 0;        // 1: cta_group::2 CTA pairs computing 256 x 256 tiles (bn == 256, BK == 64)
+  int bstat = -1;      // weight-stationary B: -1 = heuristic (whenever it fits), 0 = off, 1 = on if it fits
+  int tma_epi = -1;    // TMA-store epilogue: -1 = heuristic, 0 = off, 1 = on if the output allows it
+};
+
 struct Op {
   int kind = 0, layer = -1;
   View in, in2, out;
   // conv
   int cout = 0, cout_pad = 0, cin = 0, ksize = 0, stride = 1, pad = 0, leaky = 0, has_res = 0, out_mode = 0;
-  int Ho = 0, Wo = 0, path = PATH_TC, bn_tile = 0, bk = 0, stages = 0;
-  __nv_bfloat16* d_wt = nullptr;
+  int Ho = 0, Wo = 0, path = PATH_TC, bn_max = 0, bk = 0;
+  ConvCfg cfg;
+  int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0;   // what the last launch resolved to
+  float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
+  __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
-  alignas(64) CUtensorMap tmA, tmB, tmOut, tmRes, tmBh;   // tmBh: half-N box for the CTA-pair kernel
+  alignas(64) CUtensorMap tmA, tmOut, tmRes;
+  alignas(64) CUtensorMap tmB[4];           // weight maps with box rows 32, 64, 128, 256 (128 doubles as the pair half)
   bool tma_epi = false;
   // generic
   int factor = 0;
@@ -283,12 +296,14 @@ struct yb_engine {
   std::vector<yb_layer> plan;
   int H = 0, W = 0, C = 0, max_batch = 0, decode_mode = 0, num_classes = 0;
   bool keep_all = false;
-  int bn_max = 128;
-  bool persistent = true;
+  int bn_max = 256;
   bool b_stationary = true;
   bool tma_epilogue = true;
   bool cta_pairs = true;
+  bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
+  int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
   int num_sms = 148;
+  std::string tune_report;      // JSON written by yb_engine_autotune
   std::vector<Shape> shape;
   std::vector<View> view;
   std::vector<Buf> bufs;
@@ -327,102 +342,117 @@ static void* view_ptr(const yb_engine* e, const View& v) {
   return e->arena + e->bufs[v.buf].off + (size_t)v.coff * (v.f32 ? 4 : 2);
 }
 
-template <int BN, int BK, int ST>
-static int launch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
-  using L = ConvTcSmem<BN, BK, ST>;
-  auto kern = conv_tc_kernel<BN, BK, ST>;
-  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-  const int tiles_m = ceil_div(a.M, 128);
-  const int tiles_n = op.cout_pad / BN;
-  kern<<<tiles_m * tiles_n, CONV_TC_THREADS, L::TOTAL, st>>>(op.tmA, op.tmB, a, tiles_n);
-  YB_CUDA(cudaGetLastError());
-  return YB_OK;
-}
+static inline int bn_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3; }
 
+struct LaunchEnv {
+  int device, num_sms;
+  bool allow_bstat, allow_tma_epi, pdl;
+  int ablate;
+};
+
+// Resolves a ConvCfg into the launch parameters of conv_tc_persist_kernel<BN,BK,PAIR> and launches it.
 template <int BN, int BK, bool PAIR>
-static int launch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi) {
+static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const LaunchEnv& env, const ConvCfg& cfg) {
   auto kern = conv_tc_persist_kernel<BN, BK, PAIR>;
   const int a_bytes = 128 * BK * 2, b_bytes = (PAIR ? BN / 2 : BN) * BK * 2;
   const int num_k = a.taps * a.kc_blocks;
   PersistArgs pa;
+  memset(&pa, 0, sizeof(pa));
   const int tiles_m = PAIR ? ceil_div(ceil_div(a.M, 128), 2) : ceil_div(a.M, 128);    // pair: pairs of M tiles
-  if (PAIR) allow_bstat = false;
-  pa.n_tiles_n = op.cout_pad / BN;
+  pa.cout_pad = round_up(op.cout, BN);
+  pa.n_tiles_n = pa.cout_pad / BN;
   pa.n_tiles = tiles_m * pa.n_tiles_n;
-  pa.cout_pad = op.cout_pad;
-  // The staging buffers cost one pipeline stage at BN=256: worth it while the epilogue is the long pole
-  // (K <= 1152), not for the K-heavy 26x26/13x13 layers whose epilogue already hides behind the MMAs.
-  pa.tma_epi = (allow_tma_epi && op.tma_epi && (BN < 256 || PAIR || num_k * BK <= 1152)) ? 1 : 0;
+  pa.ablate = env.ablate;
+  // TMA-store epilogue.  Heuristic: the staging buffers cost one pipeline stage at BN=256, worth it while the epilogue
+  // is the long pole (K <= 1152) or the pair kernel halves the operand bytes anyway.
+  bool tma_epi = env.allow_tma_epi && op.tma_epi && cfg.tma_epi != 0;
+  if (cfg.tma_epi < 0) tma_epi = tma_epi && (BN < 256 || PAIR || num_k * BK <= 1152);
+  pa.tma_epi = tma_epi ? 1 : 0;
   const int budget = CONV_TCP_TILE_BUDGET - (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);
   // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
   const long long b_total = (long long)num_k * b_bytes;
-  pa.b_stationary = (allow_bstat && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= budget) ? 1 : 0;
+  pa.b_stationary = (env.allow_bstat && !PAIR && cfg.bstat != 0 && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= budget) ? 1 : 0;
   const int stage_bytes = a_bytes + (pa.b_stationary ? 0 : b_bytes);
   const int avail = budget - (pa.b_stationary ? (int)b_total : 0);
   pa.n_stages = std::min(CONV_TCP_MAX_STAGES, avail / stage_bytes);
   if (pa.n_stages < 2) return fail(YB_ERR_INVALID, "persistent conv: shared memory too small for BN=%d BK=%d", BN, BK);
   const int smem = 1024 + CONV_TCP_HEADER + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0) + (pa.b_stationary ? (int)b_total : 0) +
                    pa.n_stages * stage_bytes;
-  YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (PAIR) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    const int clusters = std::min(pa.n_tiles, num_sms / 2);
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(CONV_TCP_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    YB_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmBh, op.tmOut, op.tmRes, a, pa));
-    return YB_OK;
+  static unsigned long long attr_done = 0ull;      // per device: the opt-in shared-memory limit is set once
+  if (env.device >= 64 || !((attr_done >> env.device) & 1ull)) {
+    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
+    if (env.device < 64) attr_done |= 1ull << env.device;
   }
-  const int grid = std::min(pa.n_tiles, num_sms);
-  kern<<<grid, CONV_TCP_THREADS, smem, st>>>(op.tmA, op.tmB, op.tmOut, op.tmRes, a, pa);
-  YB_CUDA(cudaGetLastError());
+  op.launched_stages = pa.n_stages; op.launched_bstat = pa.b_stationary; op.launched_tma_epi = pa.tma_epi;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = PAIR ? dim3(2 * std::min(pa.n_tiles, env.num_sms / 2)) : dim3(std::min(pa.n_tiles, env.num_sms));
+  lc.blockDim = dim3(CONV_TCP_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (env.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  lc.attrs = attr; lc.numAttrs = na;
+  YB_CUDA(cudaLaunchKernelEx(&lc, kern, op.tmA, op.tmB[bn_index(PAIR ? BN / 2 : BN)], op.tmOut, op.tmRes, a, pa));
   return YB_OK;
 }
 
-static int dispatch_conv_tcp(cudaStream_t st, const Op& op, const ConvArgs& a, int num_sms, bool allow_bstat, bool allow_tma_epi,
-                             bool allow_pair) {
-  if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "persistent conv supports at most 1024 output channels");
-  // CTA pairs (cta_group::2) for the operand-bandwidth-bound layers: N tile 256, K >= 512
-  if (allow_pair && op.bn_tile == 256 && op.bk == 64 && a.taps * a.kc_blocks * 64 >= 512 && ceil_div(a.M, 128) >= 2)
-    return launch_conv_tcp<256, 64, true>(st, op, a, num_sms, false, allow_tma_epi);
+static int dispatch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const LaunchEnv& env, const ConvCfg& cfg) {
+  if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "tcgen05 conv supports at most %d output channels", CONV_TCP_MAX_COUT_PAD);
+  if (cfg.pair) {
+    if (cfg.bn != 256 || op.bk != 64 || ceil_div(a.M, 128) < 2) return fail(YB_ERR_INVALID, "CTA pairs need BN=256, BK=64 and two M tiles");
+    return launch_conv_tcp<256, 64, true>(st, op, a, env, cfg);
+  }
 #define YB_CASE(BN_, BK_) \
-  if (op.bn_tile == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, false>(st, op, a, num_sms, allow_bstat, allow_tma_epi);
+  if (cfg.bn == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, false>(st, op, a, env, cfg);
   YB_CASE(256, 64) YB_CASE(128, 64) YB_CASE(64, 64) YB_CASE(32, 64)
   YB_CASE(128, 32) YB_CASE(64, 32) YB_CASE(32, 32)
 #undef YB_CASE
-  return fail(YB_ERR_INVALID, "no persistent tcgen05 conv instantiation for BN=%d BK=%d", op.bn_tile, op.bk);
+  return fail(YB_ERR_INVALID, "no tcgen05 conv instantiation for BN=%d BK=%d", cfg.bn, op.bk);
 }
 
-static int stages_for(int bn, int bk) {
-  // env override for tuning; defaults keep two CTAs resident per SM where the tile allows it
-  const char* s = getenv("YB_STAGES");
-  if (s && atoi(s) > 0) return atoi(s);
-  if (bn == 256) return 4;
-  if (bn == 128 && bk == 64) return 3;
-  return 4;
+// Heuristic configuration (used until yb_engine_autotune has measured the alternatives): the widest N tile; CTA pairs
+// (cta_group::2) for the operand-bandwidth-bound layers, i.e. N tile 256 and K >= 512.
+static ConvCfg default_cfg(const Op& op, int max_batch, bool allow_pair) {
+  ConvCfg c;
+  c.bn = op.bn_max;
+  const long long M = (long long)max_batch * op.Ho * op.Wo;
+  c.pair = (allow_pair && c.bn == 256 && op.bk == 64 && op.ksize * op.ksize * op.cin >= 512 && M > 128) ? 1 : 0;
+  return c;
 }
 
-static int dispatch_conv_tc(cudaStream_t st, const Op& op, const ConvArgs& a) {
-#define YB_CASE(BN_, BK_, ST_) \
-  if (op.bn_tile == BN_ && op.bk == BK_ && op.stages == ST_) return launch_conv_tc<BN_, BK_, ST_>(st, op, a);
-  YB_CASE(256, 64, 4) YB_CASE(256, 64, 3)
-  YB_CASE(128, 64, 3) YB_CASE(128, 64, 4) YB_CASE(128, 64, 6)
-  YB_CASE(64, 64, 4) YB_CASE(64, 64, 6) YB_CASE(64, 64, 3)
-  YB_CASE(32, 64, 4) YB_CASE(32, 64, 6) YB_CASE(32, 64, 3)
-  YB_CASE(128, 32, 4) YB_CASE(128, 32, 6) YB_CASE(128, 32, 3)
-  YB_CASE(64, 32, 4) YB_CASE(64, 32, 6) YB_CASE(64, 32, 3)
-  YB_CASE(32, 32, 4) YB_CASE(32, 32, 6) YB_CASE(32, 32, 3)
-#undef YB_CASE
-  return fail(YB_ERR_INVALID, "no tcgen05 conv instantiation for BN=%d BK=%d stages=%d", op.bn_tile, op.bk, op.stages);
+// Every launch configuration worth measuring for this conv.
+static std::vector<ConvCfg> candidate_cfgs(const Op& op, int n, bool allow_pair) {
+  std::vector<ConvCfg> v;
+  const long long M = (long long)n * op.Ho * op.Wo;
+  for (int bn = op.bn_max; bn >= 32 && bn >= op.bn_max / 4; bn >>= 1) {
+    for (int pair = 0; pair <= 1; ++pair) {
+      if (pair && !(allow_pair && bn == 256 && op.bk == 64 && M > 128)) continue;
+      for (int bstat = 0; bstat <= 1; ++bstat) {
+        if (bstat && (pair || round_up(op.cout, bn) != bn)) continue;
+        for (int te = 0; te <= 1; ++te) {
+          if (te && !op.tma_epi) continue;
+          ConvCfg c;
+          c.bn = bn; c.pair = pair; c.bstat = bstat; c.tma_epi = te;
+          v.push_back(c);
+        }
+      }
+    }
+  }
+  return v;
 }
 
-static int run_op(yb_engine* e, Op& op, int n) {
+static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nullptr) {
   cudaStream_t st = e->stream;
   if (op.kind == OP_CONV) {
     ConvArgs a;
@@ -438,8 +468,10 @@ static int run_op(yb_engine* e, Op& op, int n) {
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      if (e->persistent && op.cout_pad <= 1024) YB_TRY(dispatch_conv_tcp(st, op, a, e->num_sms, e->b_stationary, e->tma_epilogue, e->cta_pairs));
-      else YB_TRY(dispatch_conv_tc(st, op, a));
+      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate};
+      ConvCfg cfg = cfg_override ? *cfg_override : op.cfg;
+      if (cfg.pair && ceil_div(a.M, 128) < 2) cfg.pair = 0;          // a batch too small to form a pair of M tiles
+      YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
       const bool mma_ok = op.ksize == 3 && op.cin == 3 && op.stride == 1 && op.cout % 32 == 0 && !op.out.f32 && !op.has_res &&
@@ -658,12 +690,12 @@ static int compile_plan(yb_engine* e) {
         int bn = 32;
         while (bn < e->bn_max && bn < op.cout) bn <<= 1;
         if (op.bk == 32 && bn > 128) bn = 128;
-        op.bn_tile = bn;
-        op.stages = stages_for(bn, op.bk);
+        op.bn_max = bn;
+        op.cfg = default_cfg(op, e->max_batch, e->cta_pairs);
       } else {
         op.path = PATH_SIMT;
       }
-      op.cout_pad = round_up(op.cout, op.path == PATH_TC ? op.bn_tile : 4);
+      op.cout_pad = round_up(op.cout, op.path == PATH_TC ? op.bn_max : 4);
       emit = true;
     } else if (l.kind == YB_MAXPOOL) {
       op.kind = OP_MAXPOOL; op.in = e->view[l.src[0]]; op.out = e->view[i]; emit = true;
@@ -755,9 +787,8 @@ static int build_tensor_maps(yb_engine* e) {
       YB_TRY(make_im2col_map(&op.tmA, in_ptr, e->max_batch, op.in.h, op.in.w, op.cin, op.in.ld, op.ksize, op.stride, op.pad, op.bk));
     }
     const int K = op.ksize * op.ksize * op.cin;
-    YB_TRY(make_tiled_map(&op.tmB, op.d_wt, op.cout_pad, K, K, op.bn_tile, op.bk));
-    memset(&op.tmBh, 0, sizeof(op.tmBh));
-    if (op.bn_tile == 256 && op.bk == 64) YB_TRY(make_tiled_map(&op.tmBh, op.d_wt, op.cout_pad, K, K, 128, op.bk));
+    memset(op.tmB, 0, sizeof(op.tmB));
+    for (int bn = 32; bn <= op.bn_max; bn <<= 1) YB_TRY(make_tiled_map(&op.tmB[bn_index(bn)], op.d_wt, op.cout_pad, K, K, bn, op.bk));
     // TMA epilogue (plain bf16 outputs): 32 rows x 32 channels per store, 64-byte swizzle
     op.tma_epi = false;
     memset(&op.tmOut, 0, sizeof(op.tmOut));
@@ -808,6 +839,97 @@ static int set_device(int device) {
 }  // namespace yb
 
 // ================================================================================================
+// autotuner
+// ================================================================================================
+// Average device time of `reps` back-to-back launches of one op (after one untimed launch), CUDA events on the engine's stream.
+static int time_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg, int reps, float* ms_out) {
+  YB_TRY(run_op(e, op, n, cfg));
+  YB_CUDA(cudaEventRecord(e->marks[6], e->stream));
+  for (int r = 0; r < reps; ++r) YB_TRY(run_op(e, op, n, cfg));
+  YB_CUDA(cudaEventRecord(e->marks[7], e->stream));
+  YB_CUDA(cudaEventSynchronize(e->marks[7]));
+  float ms = 0.f;
+  YB_CUDA(cudaEventElapsedTime(&ms, e->marks[6], e->marks[7]));
+  *ms_out = ms / (float)reps;
+  return YB_OK;
+}
+
+extern "C" {
+static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, int n, cudaEvent_t* evs, int* n_ev);
+}
+
+// Makes sure every activation buffer holds finite, realistic data for a batch of n (op timings on zeros or on
+// uninitialised memory would not be representative): one forward over pseudo-random uint8 images.
+static int prime_activations(yb_engine* e, int n) {
+  const long long total = (long long)n * e->H * e->W * e->C;
+  fill_u8_hash_kernel<<<ceil_div(total, 256), 256, 0, e->stream>>>(reinterpret_cast<unsigned char*>(e->input_dev[0]), total, 0x9E3779B9u);
+  YB_CUDA(cudaGetLastError());
+  YB_TRY(forward_impl(e, e->input_dev[0], YB_U8, YB_MEM_DEVICE, n, nullptr, nullptr));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  return YB_OK;
+}
+
+static int autotune(yb_engine* e, int n, int reps) {
+  YB_TRY(prime_activations(e, n));
+  const bool was_prof = e->prof_on;
+  e->prof_on = false;
+  struct Done { long long sig[12]; ConvCfg cfg; float best, def; };
+  std::vector<Done> done;
+  std::string& js = e->tune_report;
+  js = "{\"batch\": " + std::to_string(n) + ", \"reps\": " + std::to_string(reps) + ", \"ops\": [";
+  bool first_op = true;
+  char line[512];
+  for (size_t oi = 0; oi < e->ops.size(); ++oi) {
+    Op& op = e->ops[oi];
+    if (op.kind != OP_CONV || op.path != PATH_TC) continue;
+    const long long sig[12] = {op.cin, op.cout, op.ksize, op.stride, op.Ho, op.Wo, op.has_res, op.out_mode, op.out.f32 ? 1 : 0,
+                               op.leaky, op.in.ld, op.out.ld};
+    const Done* hit = nullptr;
+    for (const Done& d : done) if (memcmp(d.sig, sig, sizeof(sig)) == 0) { hit = &d; break; }
+    if (hit) { op.cfg = hit->cfg; op.tuned_ms = hit->best; op.default_ms = hit->def; continue; }
+    const ConvCfg def = default_cfg(op, n, e->cta_pairs);
+    float def_ms = 0.f;
+    YB_TRY(time_op(e, op, n, &def, reps, &def_ms));
+    std::vector<ConvCfg> cands = candidate_cfgs(op, n, e->cta_pairs);
+    snprintf(line, sizeof(line), "%s\n {\"op\": %d, \"layer\": %d, \"cin\": %d, \"cout\": %d, \"k\": %d, \"stride\": %d, \"ho\": %d, \"wo\": %d, "
+             "\"res\": %d, \"out_mode\": %d, \"default_ms\": %.5f, \"candidates\": [", first_op ? "" : ",", (int)oi, op.layer, op.cin, op.cout,
+             op.ksize, op.stride, op.Ho, op.Wo, op.has_res, op.out_mode, def_ms);
+    js += line;
+    first_op = false;
+    float best = 1e30f;
+    ConvCfg best_cfg = def;
+    for (size_t ci = 0; ci < cands.size(); ++ci) {
+      float ms = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {       // best of three short bursts
+        float t = 0.f;
+        YB_TRY(time_op(e, op, n, &cands[ci], reps, &t));
+        ms = std::min(ms, t);
+      }
+      snprintf(line, sizeof(line), "%s{\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"stages\": %d, \"ms\": %.5f}", ci ? ", " : "",
+               cands[ci].bn, cands[ci].pair, op.launched_bstat, op.launched_tma_epi, op.launched_stages, ms);
+      js += line;
+      if (ms < best) { best = ms; best_cfg = cands[ci]; }
+    }
+    // keep the heuristic unless a candidate is measurably (>1.5%) faster: avoids flapping on noise
+    float def_best = def_ms;
+    for (int rep = 0; rep < 2; ++rep) { float t = 0.f; YB_TRY(time_op(e, op, n, &def, reps, &t)); def_best = std::min(def_best, t); }
+    if (best > def_best * 0.985f) { best_cfg = def; best = def_best; }
+    snprintf(line, sizeof(line), "], \"chosen\": {\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"ms\": %.5f}}", best_cfg.bn, best_cfg.pair,
+             best_cfg.bstat, best_cfg.tma_epi, best);
+    js += line;
+    op.cfg = best_cfg; op.tuned_ms = best; op.default_ms = def_best;
+    Done d;
+    memcpy(d.sig, sig, sizeof(sig)); d.cfg = best_cfg; d.best = best; d.def = def_best;
+    done.push_back(d);
+  }
+  js += "\n]}";
+  e->prof_on = was_prof;
+  e->last_n = 0;            // activations were clobbered: a forward must precede the next read/detect
+  e->detected = false;
+  return YB_OK;
+}
+
+// ================================================================================================
 // C ABI
 // ================================================================================================
 extern "C" {
@@ -835,9 +957,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   e->plan.assign(plan, plan + n_layers);
   const char* ka = getenv("YB_KEEP_ALL");
   e->keep_all = ka && atoi(ka) != 0;
-  const char* ps = getenv("YB_PERSIST");
-  if (ps) e->persistent = atoi(ps) != 0;
-  if (e->persistent) e->bn_max = 256;
+  const char* pd = getenv("YB_PDL");
+  if (pd) e->pdl = atoi(pd) != 0;
   const char* cp = getenv("YB_PAIR");
   if (cp) e->cta_pairs = atoi(cp) != 0;
   const char* te = getenv("YB_TMA_EPI");
@@ -1124,6 +1245,62 @@ int yb_engine_set_conv_impl(yb_engine* e, int impl) {
   return YB_OK;
 }
 
+int yb_engine_autotune(yb_engine* e, int n, int reps) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
+  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_autotune before yb_engine_load_weights");
+  YB_TRY(set_device(e->device));
+  return autotune(e, n, reps > 0 ? reps : 5);
+}
+
+int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* needed) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  const size_t need = e->tune_report.size() + 1;
+  if (needed) *needed = need;
+  if (!buf) return YB_OK;
+  if (capacity < need) return fail(YB_ERR_CAPACITY, "tune report needs %zu bytes, buffer holds %zu", need, capacity);
+  memcpy(buf, e->tune_report.c_str(), need);
+  return YB_OK;
+}
+
+int yb_engine_set_option(yb_engine* e, const char* name, int value) {
+  if (!e || !name) return fail(YB_ERR_INVALID, "yb_engine_set_option: bad argument");
+  if (!strcmp(name, "pdl")) e->pdl = value != 0;
+  else if (!strcmp(name, "ablate")) e->ablate = value & 15;
+  else if (!strcmp(name, "bstat")) e->b_stationary = value != 0;
+  else if (!strcmp(name, "tma_epi")) e->tma_epilogue = value != 0;
+  else if (!strcmp(name, "pairs")) {
+    e->cta_pairs = value != 0;
+    for (Op& op : e->ops) if (op.kind == OP_CONV && op.path == PATH_TC) op.cfg = default_cfg(op, e->max_batch, e->cta_pairs);
+  } else return fail(YB_ERR_INVALID, "unknown option '%s'", name);
+  return YB_OK;
+}
+
+int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi) {
+  if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_set_conv_cfg: bad argument");
+  Op& op = e->ops[op_index];
+  if (op.kind != OP_CONV || op.path != PATH_TC) return fail(YB_ERR_INVALID, "op %d is not a tcgen05 conv", op_index);
+  if (bn == 0) { op.cfg = default_cfg(op, e->max_batch, e->cta_pairs); return YB_OK; }
+  if ((bn != 32 && bn != 64 && bn != 128 && bn != 256) || bn > op.bn_max) return fail(YB_ERR_INVALID, "op %d: N tile %d not available (max %d)", op_index, bn, op.bn_max);
+  if (pair && (bn != 256 || op.bk != 64)) return fail(YB_ERR_INVALID, "op %d: CTA pairs need BN=256 and BK=64", op_index);
+  op.cfg.bn = bn; op.cfg.pair = pair ? 1 : 0; op.cfg.bstat = bstat; op.cfg.tma_epi = tma_epi;
+  return YB_OK;
+}
+
+int yb_engine_time_op(yb_engine* e, int op_index, int n, int reps, float* ms) {
+  if (!e || !ms || op_index < 0 || op_index >= (int)e->ops.size() || reps <= 0) return fail(YB_ERR_INVALID, "yb_engine_time_op: bad argument");
+  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
+  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_time_op before yb_engine_load_weights");
+  YB_TRY(set_device(e->device));
+  if (e->cur_input == nullptr) YB_TRY(prime_activations(e, n));
+  const bool was_prof = e->prof_on;
+  e->prof_on = false;
+  const int r = time_op(e, e->ops[op_index], n, nullptr, reps, ms);
+  e->prof_on = was_prof;
+  e->last_n = 0; e->detected = false;
+  return r;
+}
+
 int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches) {
   if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
   if (forward_launches) *forward_launches = e->fwd_launches;
@@ -1199,10 +1376,21 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   const Op& op = e->ops[op_index];
   if (layer) *layer = op.layer;
   if (path) *path = op.kind == OP_CONV ? op.path : -1 - op.kind;
-  if (bn_tile) *bn_tile = op.bn_tile;
+  if (bn_tile) *bn_tile = op.cfg.bn;
   if (bk) *bk = op.bk;
-  if (stages) *stages = op.stages;
+  if (stages) *stages = op.launched_stages;
   if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin : 0.0;
+  return YB_OK;
+}
+
+int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages) {
+  if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_op_cfg: bad argument");
+  const Op& op = e->ops[op_index];
+  if (bn) *bn = op.cfg.bn;
+  if (pair) *pair = op.cfg.pair;
+  if (bstat) *bstat = op.launched_bstat;
+  if (tma_epi) *tma_epi = op.launched_tma_epi;
+  if (stages) *stages = op.launched_stages;
   return YB_OK;
 }
 

@@ -151,8 +151,40 @@ class Engine(object):
         return {"layer": layer.value, "path": path.value, "bn": bn.value, "bk": bk.value, "stages": st.value,
                 "flops_per_image": fl.value}
 
+    def op_cfg(self, op_index):
+        v = [ctypes.c_int() for _ in range(5)]
+        _lib.check(_lib.lib().yb_engine_op_cfg(self._h, op_index, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("bn", "pair", "bstat", "tma_epi", "stages"), [x.value for x in v]))
+
     def set_conv_impl(self, impl):
         _lib.check(_lib.lib().yb_engine_set_conv_impl(self._h, impl))
+
+    def autotune(self, n=None, reps=5):
+        """Times every launch configuration of each tcgen05 conv on the device for a batch of n and keeps the fastest.
+        Returns the report (dict).  Outputs are unchanged; the activations are clobbered until the next forward."""
+        import json
+        _lib.check(_lib.lib().yb_engine_autotune(self._h, int(n or self.max_batch), int(reps)))
+        self.last_n = 0
+        return json.loads(self.tune_report())
+
+    def tune_report(self):
+        need = ctypes.c_size_t(0)
+        _lib.check(_lib.lib().yb_engine_tune_report(self._h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        _lib.check(_lib.lib().yb_engine_tune_report(self._h, buf, need.value, None))
+        return buf.value.decode("utf-8") or "{}"
+
+    def set_option(self, name, value):
+        _lib.check(_lib.lib().yb_engine_set_option(self._h, name.encode("ascii"), int(value)))
+
+    def set_conv_cfg(self, op_index, bn, pair=0, bstat=-1, tma_epi=-1):
+        _lib.check(_lib.lib().yb_engine_set_conv_cfg(self._h, op_index, bn, pair, bstat, tma_epi))
+
+    def time_op(self, op_index, n=None, reps=10):
+        ms = ctypes.c_float()
+        _lib.check(_lib.lib().yb_engine_time_op(self._h, op_index, int(n or self.max_batch), reps, ctypes.byref(ms)))
+        self.last_n = 0
+        return ms.value
 
     def launch_count(self):
         a, b = ctypes.c_int(), ctypes.c_int()

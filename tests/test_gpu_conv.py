@@ -154,3 +154,43 @@ def test_session_run_matches_reference_protocol():
         out = sess.run(net[-1].out, feed_dict={net[0].out: x})
     assert out.shape == (2, 252, 85) and out.dtype == np.float32
     assert helpers.rel_err(out, convstack.forward(topo, stream, x)) <= TOL
+
+
+def test_autotune_keeps_results_bit_identical():
+    """Every launch configuration walks K in the same order, so tuning must not change a single output bit;
+    the same holds for programmatic dependent launch on/off."""
+    shape = (96, 64, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=2)
+    x = synth.images(3, shape[0], shape[1], seed=5)
+    eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 3, stream)
+    eng.forward(x)
+    y0 = eng.read_output()
+    report = eng.autotune(3, reps=2)
+    assert len(report["ops"]) >= 10 and all(len(o["candidates"]) >= 2 for o in report["ops"])
+    with pytest.raises(Exception):
+        eng.read_output()                     # activations were clobbered: a forward has to come first
+    eng.forward(x)
+    assert np.array_equal(eng.read_output(), y0)
+    eng.set_option("pdl", 0)
+    eng.forward(x)
+    assert np.array_equal(eng.read_output(), y0)
+    eng.set_option("pdl", 1)
+    # forced configurations: every N tile / pair / stationary / epilogue variant of one mid-network conv
+    n_ops = len(eng.profile(x))
+    tc_ops = [i for i in range(n_ops) if eng.op_info(i)["path"] == 0]
+    for op_i in tc_ops[3:40:6]:
+        for bn in (32, 64, 128, 256):
+            for pair in (0, 1):
+                for bstat in (0, 1):
+                    for te in (0, 1):
+                        try:
+                            eng.set_conv_cfg(op_i, bn, pair, bstat, te)
+                        except Exception:
+                            continue          # not available for this layer (N tile wider than Cout, pair without BN=256)
+                        eng.forward(x)
+                        assert np.array_equal(eng.read_output(), y0), (op_i, bn, pair, bstat, te)
+        eng.set_conv_cfg(op_i, 0)
+    with pytest.raises(Exception):
+        eng.set_option("no_such_option", 1)
+    assert eng.time_op(tc_ops[0], 3, 2) > 0.0
+    eng.close()

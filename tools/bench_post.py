@@ -1,0 +1,64 @@
+"""GPU measurement tool (not a test): BASELINE config 5 -- decode + NMS isolated.
+
+  python tools/bench_post.py [--batch 1024] [--out gpurun_out/post_c5.json]
+
+Head tensor [batch, 10647, 85] float32, N(0,1) logits, resident in HBM; score threshold 0.001 (every row is a
+candidate: K = 10,647 per image, 56.7 M IoU pairs at most), IoU threshold 0.6.  Also the sparse variant (objectness
+logits N(-6,2), ~tens of candidates per image).  Reports device milliseconds per stage (CUDA events inside
+yb_post_run), decode GB/s against the measured HBM peak, and NMS images/s.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+from tensorflow_yolo_b200 import engine as yb  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "post_c5.json"))
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    B, R, L = args.batch, 10647, 85
+    anchors = np.reshape(bench.V3_ANCHORS, [-1, 2]).astype(np.float64)
+    scales = []
+    for i, (g, stride) in enumerate(((13, 32), (26, 16), (52, 8))):
+        a = anchors[[6, 7, 8]] if i == 0 else anchors[[3, 4, 5]] if i == 1 else anchors[[0, 1, 2]]
+        scales.append((g, g, [(aw / stride, ah / stride) for aw, ah in a]))
+    post = yb.PostProcessor(scales, 80, yb.YB_DECODE_V3, max_batch=B)
+    peaks = bench.load_peaks()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    head = torch.randn((B, R, L), device="cuda", dtype=torch.float32, generator=gen)
+    out = {"batch": B, "rows": R, "box_len": L, "head_bytes": B * R * L * 4}
+    for name, thr, shift in (("dense_thr0.001", 0.001, None), ("sparse_obj_N(-6,2)_thr0.5", 0.5, (-6.0, 2.0))):
+        if shift is not None:
+            head[:, :, 4] = head[:, :, 4] * shift[1] + shift[0]
+        best = None
+        for _ in range(args.reps):
+            post.run(head, thr, 0.6, fetch=False)
+            post.sync()
+            d, n = post.last_ms()
+            if best is None or d + n < best[0] + best[1]:
+                best = (d, n)
+        kept = post.run(head[:4], thr, 0.6)
+        row = {"decode_ms": best[0], "nms_ms": best[1], "decode_GBps": B * R * L * 4 / (best[0] * 1e-3) / 1e9,
+               "decode_frac_of_hbm_peak": B * R * L * 4 / (best[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+               "images_per_s": B / ((best[0] + best[1]) * 1e-3), "candidates_img0": int(post.last_candidates[0]),
+               "kept_first4": [len(k) for k in kept]}
+        out[name] = row
+        print(name, row, flush=True)
+    with open(args.out, "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
