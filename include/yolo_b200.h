@@ -157,9 +157,13 @@ int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* need
  * 1 = no epilogue work, 2 = no MMAs, 4 = no activation loads, 8 = no weight loads; outputs are wrong while set). */
 int yb_engine_set_option(yb_engine* e, const char* name, int value);
 /* Forces the launch configuration of launched op `op_index` (bn = 0 restores the heuristic; bstat / tma_epi: -1 =
- * heuristic, 0 = off, 1 = on when possible) and times one op in isolation (average of reps launches, milliseconds). */
-int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi);
+ * heuristic, 0 = off, 1 = on when possible; ksub = BK-blocks per pipeline stage, 0 = heuristic) and times one op in isolation (average of reps launches, milliseconds). */
+int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi, int ksub);
 int yb_engine_time_op(yb_engine* e, int op_index, int n, int reps, float* ms);
+/* With option "cycles" = 1 the conv kernel accumulates SM cycle counters per role, summed over CTAs and launches
+ * (producer: wait-for-free-stage, total; MMA issuer: wait-for-data, wait-for-accumulator, total; epilogue warps:
+ * wait-for-accumulator, wait-for-residual, wait-for-staging-buffer, TMEM load, math+store, total).  out16: 16 values. */
+int yb_engine_read_cycles(yb_engine* e, unsigned long long* out16, int reset);
 /* number of kernel launches the last forward / detect enqueued */
 int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches);
 
@@ -184,8 +188,8 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
                       double* flops_per_image);
 
 /* Launch configuration of op `op_index` as resolved by its last launch: N tile, CTA pairs, weight-stationary B,
- * TMA-store epilogue, pipeline stages. */
-int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages);
+ * TMA-store epilogue, pipeline stages, BK-blocks per stage. */
+int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages, int* ksub);
 
 /* ---- stand-alone post-processing on caller tensors ---- */
 typedef struct yb_scale {

@@ -61,8 +61,9 @@ _SIGNATURES = {
     "yb_engine_tune_report": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _P(ctypes.c_size_t)]),
     "yb_engine_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "yb_engine_set_conv_cfg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                              ctypes.c_int]),
+                                              ctypes.c_int, ctypes.c_int]),
     "yb_engine_time_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
+    "yb_engine_read_cycles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_launch_count": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int), _P(ctypes.c_int)]),
     "yb_engine_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
@@ -73,7 +74,7 @@ _SIGNATURES = {
                                               _P(ctypes.c_int), _P(ctypes.c_int)]),
     "yb_engine_op_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_int),
                                          _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_double)]),
-    "yb_engine_op_cfg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [_P(ctypes.c_int)] * 5),
+    "yb_engine_op_cfg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [_P(ctypes.c_int)] * 6),
     "yb_post_create": (ctypes.c_int, [_P(yb_scale), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _P(ctypes.c_void_p)]),
     "yb_post_destroy": (None, [ctypes.c_void_p]),

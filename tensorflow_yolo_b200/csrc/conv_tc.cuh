@@ -278,29 +278,42 @@ constexpr int CONV_TCP_EPI_BYTES = CONV_TCP_EPI_WARPS * 2 * CONV_TCP_EPI_BUF;
 struct PersistArgs {
   int n_tiles_n, n_tiles, cout_pad;
   int n_stages;        // pipeline depth (runtime: fills the shared memory that is left)
+  int ksub;            // BK-blocks per pipeline stage: one barrier round trip (and one pass of the issue loop) feeds
+                       // ksub * BK/16 MMAs, so narrow tiles still give the tensor pipe >= ~500 cycles per hand-shake
   int b_stationary;    // 1: the whole [BN x K] weight matrix is loaded once per CTA and stays in shared memory
   int tma_epi;         // 1: bf16 plain output through smem + TMA store, residual through TMA load
   int ablate;          // debug/roofline probes (results are wrong when non-zero): 1 = epilogue does nothing,
                        // 2 = no MMAs, 4 = no A loads, 8 = no B loads
+  unsigned long long* dbg;   // optional [16] cycle counters summed over all CTAs (see CONV_DBG_*); nullptr = off
 };
+// cycle counters: who waits on whom inside the persistent conv kernel
+enum ConvDbg {
+  CONV_DBG_PROD_WAIT_EMPTY = 0, CONV_DBG_PROD_TOTAL, CONV_DBG_MMA_WAIT_FULL, CONV_DBG_MMA_WAIT_TMEM, CONV_DBG_MMA_TOTAL,
+  CONV_DBG_EPI_WAIT_ACC, CONV_DBG_EPI_WAIT_RES, CONV_DBG_EPI_WAIT_BUF, CONV_DBG_EPI_TMEM_LD, CONV_DBG_EPI_MATH_STORE,
+  CONV_DBG_EPI_TOTAL, CONV_DBG_EPI_FENCE_STORE, CONV_DBG_COUNT
+};
+__device__ __forceinline__ long long clk() { return clock64(); }
 
-// PAIR = true: launched as 2-CTA clusters.  The pair computes a 256(M) x 256(N) tile with tcgen05.mma.cta_group::2:
-// CTA r holds the A rows of M tile 2j+r and the B rows [128r, 128r+128) of the N tile, so every SM ingests 32 KB
-// per K step instead of 48 KB; the leader (rank 0) issues the MMAs, both CTAs' TMA loads complete on the leader's
-// full barriers, the leader's commits release the smem stages / publish the accumulators in both CTAs, and both
-// CTAs' epilogue warps hand the accumulator back on the leader's tmem_empty barrier.
+// PAIR = true: launched as 2-CTA clusters.  The pair computes a 256(M) x BN(N) tile with tcgen05.mma.cta_group::2:
+// CTA r holds the A rows of M tile 2j+r and the B rows [r*BN/2, (r+1)*BN/2) of the N tile, so every SM ingests half
+// of B per K step (BN=256: 32 KB instead of 48 KB) and one MMA instruction covers 256 rows -- issuing an MMA costs
+// ~120 cycles whatever its shape, which is what bounds the narrow-N layers.  The leader (rank 0) issues the MMAs, both
+// CTAs' TMA loads complete on the leader's full barriers, the leader's commits release the smem stages / publish the
+// accumulators in both CTAs, and both CTAs' epilogue warps hand the accumulator back on the leader's tmem_empty barrier.
 template <int BN, int BK, bool PAIR>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a,
                        const PersistArgs pa) {
-  static_assert(!PAIR || BN == 256, "the CTA pair computes 256 x 256 tiles");
+  static_assert(!PAIR || BN >= 64, "cta_group::2 needs N >= 64 here (32 B rows per CTA)");
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;      // bytes of B this CTA loads per K step
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles.  The offset is added to the __shared__ array itself (not to an
+  // integer-cast pointer) so the compiler keeps every access in the shared address space (LDS/STS, not generic LD/ST).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + CONV_TCP_MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + CONV_TCP_MAX_STAGES;    // [2]
@@ -316,7 +329,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* epi_smem = smem + CONV_TCP_HEADER;                                 // CONV_TCP_EPI_BYTES when tma_epi
   uint8_t* b_stat = epi_smem + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);        // num_k * B_BYTES when stationary
   uint8_t* stages = b_stat + (bstat ? num_k * B_BYTES : 0);
-  const int stage_bytes = A_BYTES + (bstat ? 0 : B_BYTES);
+  const int sub_bytes = A_BYTES + (bstat ? 0 : B_BYTES);      // one BK-block of A (and B) inside a stage
+  const int ksub = pa.ksub;
+  const int stage_bytes = ksub * sub_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -333,7 +348,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], (PAIR ? 2 : 1) * CONV_TCP_EPI_WARPS);
     }
-    mbar_init(b_full_bar, 1);
+    mbar_init(b_full_bar, PAIR ? 2 : 1);
     for (int s = 0; s < 2 * CONV_TCP_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
     if (pa.tma_epi) {
       tma_prefetch_desc(&tmOut);
@@ -362,12 +377,22 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       if (bstat) {      // weights do not depend on the previous kernel: fetched before the grid dependency resolves
-        mbar_expect_tx(b_full_bar, (uint32_t)(num_k * B_BYTES));
-        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, b_full_bar, b_stat + kb * B_BYTES, kb * BK, 0);
+        if (PAIR) {     // each CTA keeps its half of the N tile; both halves complete on the leader's barrier
+          const uint32_t bb = mapa_u32(smem_u32(b_full_bar), 0);
+          if (rank == 0) mbar_expect_tx(b_full_bar, 2u * (uint32_t)(num_k * B_BYTES));
+          else mbar_arrive_cluster(bb);
+          for (int kb = 0; kb < num_k; ++kb) tma_load_2d_pair(&tmB, bb, b_stat + kb * B_BYTES, kb * BK, (int)rank * (BN / 2));
+        } else {
+          mbar_expect_tx(b_full_bar, (uint32_t)(num_k * B_BYTES));
+          for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, b_full_bar, b_stat + kb * B_BYTES, kb * BK, 0);
+        }
       }
       griddep_wait();
       const bool load_a = !(pa.ablate & 4), load_b = !bstat && !(pa.ablate & 8);
       const uint32_t tx_bytes = (load_a ? (uint32_t)A_BYTES : 0u) + (load_b ? (uint32_t)B_BYTES : 0u);
+      const bool dbg = pa.dbg != nullptr;
+      long long t_wait = 0;
+      const long long t_begin = dbg ? clk() : 0;
       int stage = 0;
       uint32_t phase = 0;
       const int hw = a.Ho * a.Wo;
@@ -386,76 +411,110 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           base_h = p0 * a.conv_stride - a.pad;
         }
         int cb = 0, kh = 0, kw = 0;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb0 = 0; kb0 < num_k; kb0 += ksub) {
+          const int cnt = (num_k - kb0 < ksub) ? num_k - kb0 : ksub;      // BK-blocks in this stage
+          const long long t0 = dbg ? clk() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = stages + stage * stage_bytes;
+          if (dbg) t_wait += clk() - t0;
+          uint8_t* st_base = stages + stage * stage_bytes;
+          const uint32_t fb = PAIR ? full0 + (uint32_t)stage * 8u : 0u;
           if (PAIR) {
-            const uint32_t fb = full0 + (uint32_t)stage * 8u;
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes);   // bytes of both CTAs
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes * (uint32_t)cnt);   // bytes of both CTAs
             else mbar_arrive_cluster(fb);
-            if (load_a) {
-              if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-              else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
-            }
-            if (load_b) tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
           } else {
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (load_a) {
-              if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-              else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
-            }
-            if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+            mbar_expect_tx(&full_bar[stage], tx_bytes * (uint32_t)cnt);
           }
-          if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+          for (int j = 0; j < cnt; ++j) {
+            uint8_t* sa = st_base + j * sub_bytes;
+            const int kb = kb0 + j;
+            if (PAIR) {
+              if (load_a) {
+                if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+                else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
+              }
+              if (load_b) tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
+            } else {
+              if (load_a) {
+                if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+                else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+              }
+              if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+            }
+            if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+          }
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
+      }
+      if (dbg) {
+        atomicAdd(&pa.dbg[CONV_DBG_PROD_WAIT_EMPTY], (unsigned long long)t_wait);
+        atomicAdd(&pa.dbg[CONV_DBG_PROD_TOTAL], (unsigned long long)(clk() - t_begin));
       }
     }
   } else if (warp == 1 && rank == 0) {
     // ------------------------------ MMA issuer (pair: leader CTA only) ------------------------------
-    constexpr uint32_t idesc = PAIR ? make_idesc_m<BN, 256>() : make_idesc<BN>();
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    if (bstat) {
-      mbar_wait(b_full_bar, 0);
-      tc_fence_after();
-    }
-    const uint32_t b_stat_addr = smem_u32(b_stat);
-    for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // One elected thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions; keeping the
+    // other 31 lanes out of the loop removes the per-step elect / reconvergence overhead).
+    if (elect_one()) {
+      constexpr uint32_t idesc = PAIR ? make_idesc_m<BN, 256>() : make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      if (bstat) {
+        mbar_wait(b_full_bar, 0);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(stages + stage * stage_bytes);
-          const uint64_t da = make_kmajor_desc<BK>(sa);
-          const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)(kb * B_BYTES) : sa + A_BYTES);
-          const bool do_mma = !(pa.ablate & 2);
-          if (PAIR) {
-            if (do_mma) {
+      }
+      const uint32_t b_stat_addr = smem_u32(b_stat);
+      const uint32_t stages_addr = smem_u32(stages);
+      const bool do_mma = !(pa.ablate & 2);
+      const bool dbg = pa.dbg != nullptr;
+      long long t_full = 0, t_tmem = 0;
+      const long long t_begin = dbg ? clk() : 0;
+      for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        long long t0 = dbg ? clk() : 0;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
+        if (dbg) t_tmem += clk() - t0;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb0 = 0; kb0 < num_k; kb0 += ksub) {
+          const int cnt = (num_k - kb0 < ksub) ? num_k - kb0 : ksub;
+          t0 = dbg ? clk() : 0;
+          mbar_wait(&full_bar[stage], phase);
+          if (dbg) t_full += clk() - t0;
+          tc_fence_after();
+          const uint32_t st_base = stages_addr + (uint32_t)(stage * stage_bytes);
+          if (do_mma) {
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t sa = st_base + (uint32_t)(j * sub_bytes);
+              const uint64_t da = make_kmajor_desc<BK>(sa);
+              const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)((kb0 + j) * B_BYTES) : sa + A_BYTES);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
+                const uint32_t accum = ((kb0 + j) | k) != 0 ? 1u : 0u;
+                if (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+                else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+              }
             }
-            umma_commit_pair(&empty_bar[stage], 3);
-            if (kb == num_k - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
-          } else {
-            if (do_mma) {
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[stage]);
-            if (kb == num_k - 1) umma_commit(&tmem_full_bar[acc]);
           }
+          if (PAIR) {
+            umma_commit_pair(&empty_bar[stage], 3);                          // frees this smem stage in both CTAs
+            if (kb0 + cnt == num_k) umma_commit_pair(&tmem_full_bar[acc], 3);  // accumulator complete
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb0 + cnt == num_k) umma_commit(&tmem_full_bar[acc]);
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+      if (dbg) {
+        atomicAdd(&pa.dbg[CONV_DBG_MMA_WAIT_FULL], (unsigned long long)t_full);
+        atomicAdd(&pa.dbg[CONV_DBG_MMA_WAIT_TMEM], (unsigned long long)t_tmem);
+        atomicAdd(&pa.dbg[CONV_DBG_MMA_TOTAL], (unsigned long long)(clk() - t_begin));
       }
     }
+    __syncwarp();
   } else if (warp >= 2) {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;
@@ -463,16 +522,22 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t tmem_empty0 = PAIR ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0u;   // leader's tmem_empty_bar[0]
     constexpr int NCH = BN / 32;                      // 32-column chunks per tile
     constexpr int CH_PER = (NCH + 1) / 2;
-    const int ch_begin = half * CH_PER;
-    const int ch_end = (ch_begin + CH_PER < NCH) ? ch_begin + CH_PER : NCH;
+    const int ch_begin0 = half * CH_PER;
+    const int ch_end0 = (ch_begin0 + CH_PER < NCH) ? ch_begin0 + CH_PER : NCH;
     const int hw = a.Ho * a.Wo;
     int it = 0;
     int epi_idx = 0;            // running sub-tile counter of this warp (selects the staging buffer)
     uint32_t res_par = 0;       // phase bits of this warp's two residual barriers
     griddep_wait();             // residual reads and output stores must follow the previous kernels
+    const bool dbg = pa.dbg != nullptr;
+    long long t_acc = 0, t_res = 0, t_buf = 0, t_ld = 0, t_math = 0, t_fs = 0;
+    const long long t_begin = dbg ? clk() : 0;
     for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      // a 32-column tile has a single chunk per lane quarter: the two warps of a quarter take alternate tiles
+      const int ch_begin = (NCH == 1) ? 0 : ch_begin0;
+      const int ch_end = (NCH == 1) ? (((it & 1) == half) ? 1 : 0) : ch_end0;
       if (pa.ablate & 1) {      // probe: accumulator handed straight back
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
@@ -525,7 +590,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tma_load_2d(&tmRes, &rbar[b], bufs + b * CONV_TCP_EPI_BUF, n0 + chunk * 32, m_warp);
         };
         if (has_res_t && ch_begin < ch_end && lane == 0) issue_res(ch_begin, epi_idx);
+        long long t0 = dbg ? clk() : 0;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (dbg) t_acc += clk() - t0;
         tc_fence_after();
 #pragma unroll 1
         for (int chunk = ch_begin; chunk < ch_end; ++chunk, ++epi_idx) {
@@ -535,16 +602,23 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
           uint4 rcur[4];
           if (has_res_t) {
+            t0 = dbg ? clk() : 0;
             if (chunk + 1 < ch_end && lane == 0) issue_res(chunk + 1, epi_idx + 1);
+            if (dbg) { const long long t1 = clk(); t_buf += t1 - t0; t0 = t1; }
             mbar_wait(&rbar[b], (res_par >> b) & 1u);
+            if (dbg) t_res += clk() - t0;
             res_par ^= (1u << b);
 #pragma unroll
             for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(buf + row_off + (((uint32_t)g ^ sw) << 4));
           } else {
+            t0 = dbg ? clk() : 0;
             if (lane == 0) tma_store_wait_read<1>();                     // the store two steps ago used this buffer
             __syncwarp();
+            if (dbg) t_buf += clk() - t0;
           }
+          t0 = dbg ? clk() : 0;
           tmem_ld_wait();
+          if (dbg) { const long long t1 = clk(); t_ld += t1 - t0; t0 = t1; }
           const int cbase = n0 + chunk * 32;
           float f[32];
 #pragma unroll
@@ -564,6 +638,30 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               }
             }
           }
+          if (a.out_f32) {
+            // fp32 heads: the 32-column chunk goes out as two stores of 16 floats (64-byte rows, same staging buffers)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint8_t* hb = bufs + ((epi_idx + hf) & 1) * CONV_TCP_EPI_BUF;
+              if (hf == 1) {
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<float4*>(hb + row_off + (((uint32_t)g ^ sw) << 4)) =
+                    make_float4(f[hf * 16 + g * 4], f[hf * 16 + g * 4 + 1], f[hf * 16 + g * 4 + 2], f[hf * 16 + g * 4 + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmOut, hb, cbase + hf * 16, m_warp);
+                tma_store_commit();
+              }
+            }
+            ++epi_idx;               // two staging buffers were consumed (the loop header adds the other one)
+            if (dbg) t_fs += clk() - t0;
+            continue;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
@@ -577,12 +675,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             pk.w = *reinterpret_cast<uint32_t*>(&b3);
             *reinterpret_cast<uint4*>(buf + row_off + (((uint32_t)g ^ sw) << 4)) = pk;
           }
+          if (dbg) { const long long t1 = clk(); t_math += t1 - t0; t0 = t1; }
           fence_proxy_async();                 // make the generic-proxy smem writes visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmOut, buf, cbase, m_warp);    // rows >= the tensor's row count and channels >= Cout are clipped
             tma_store_commit();
           }
+          if (dbg) t_fs += clk() - t0;
         }
         tc_fence_before();
         __syncwarp();
@@ -675,6 +775,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
       }
+    }
+    if (dbg && lane == 0) {
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_WAIT_ACC], (unsigned long long)t_acc);
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_WAIT_RES], (unsigned long long)t_res);
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_WAIT_BUF], (unsigned long long)t_buf);
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_TMEM_LD], (unsigned long long)t_ld);
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_MATH_STORE], (unsigned long long)t_math);
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_TOTAL], (unsigned long long)(clk() - t_begin));
+      atomicAdd(&pa.dbg[CONV_DBG_EPI_FENCE_STORE], (unsigned long long)t_fs);
     }
   }
   if (pa.tma_epi && warp >= 2 && lane == 0) tma_store_wait_all();

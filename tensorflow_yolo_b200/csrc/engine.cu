@@ -100,6 +100,19 @@ static int make_map_2d(CUtensorMap* tm, const void* base, long long rows, int co
   return YB_OK;
 }
 
+static int make_map_2d_f32(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_rows, int box_cols,
+                           CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (%d): rows=%lld cols=%d ld=%d box=%dx%d", (int)r, rows, cols, ld, box_rows, box_cols);
+  return YB_OK;
+}
+
 static CUtensorMapSwizzle swizzle_for(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; }
 
 // [rows, cols] bf16 row-major with row pitch ld (elements); box = box_rows x bk
@@ -256,9 +269,10 @@ enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2 };
 // fastest measured candidate.
 struct ConvCfg {
   int bn = 0;          // N tile (TMEM columns per accumulator): 32, 64, 128 or 256
-  int pair = 0;        // 1: cta_group::2 CTA pairs computing 256 x 256 tiles (bn == 256, BK == 64)
+  int pair = 0;        // 1: cta_group::2 CTA pairs computing 256 x bn tiles (bn >= 64)
   int bstat = -1;      // weight-stationary B: -1 = heuristic (whenever it fits), 0 = off, 1 = on if it fits
   int tma_epi = -1;    // TMA-store epilogue: -1 = heuristic, 0 = off, 1 = on if the output allows it
+  int ksub = 0;        // BK-blocks per pipeline stage: 0 = heuristic (enough MMA work per barrier hand-shake)
 };
 
 struct Op {
@@ -268,7 +282,7 @@ struct Op {
   int cout = 0, cout_pad = 0, cin = 0, ksize = 0, stride = 1, pad = 0, leaky = 0, has_res = 0, out_mode = 0;
   int Ho = 0, Wo = 0, path = PATH_TC, bn_max = 0, bk = 0;
   ConvCfg cfg;
-  int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0;   // what the last launch resolved to
+  int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0;   // what the last launch resolved to
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
   __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
@@ -302,6 +316,7 @@ struct yb_engine {
   bool cta_pairs = true;
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
   int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
+  unsigned long long* dbg_counters = nullptr;   // device [CONV_DBG_COUNT] cycle counters while "cycles" is switched on
   int num_sms = 148;
   std::string tune_report;      // JSON written by yb_engine_autotune
   std::vector<Shape> shape;
@@ -348,6 +363,7 @@ struct LaunchEnv {
   int device, num_sms;
   bool allow_bstat, allow_tma_epi, pdl;
   int ablate;
+  unsigned long long* dbg;
 };
 
 // Resolves a ConvCfg into the launch parameters of conv_tc_persist_kernel<BN,BK,PAIR> and launches it.
@@ -363,6 +379,7 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
   pa.n_tiles_n = pa.cout_pad / BN;
   pa.n_tiles = tiles_m * pa.n_tiles_n;
   pa.ablate = env.ablate;
+  pa.dbg = env.dbg;
   // TMA-store epilogue.  Heuristic: the staging buffers cost one pipeline stage at BN=256, worth it while the epilogue
   // is the long pole (K <= 1152) or the pair kernel halves the operand bytes anyway.
   bool tma_epi = env.allow_tma_epi && op.tma_epi && cfg.tma_epi != 0;
@@ -371,9 +388,28 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
   const int budget = CONV_TCP_TILE_BUDGET - (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0);
   // weight-stationary when one N tile covers Cout and at least 4 A stages still fit next to the weights
   const long long b_total = (long long)num_k * b_bytes;
-  pa.b_stationary = (env.allow_bstat && !PAIR && cfg.bstat != 0 && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= budget) ? 1 : 0;
-  const int stage_bytes = a_bytes + (pa.b_stationary ? 0 : b_bytes);
+  pa.b_stationary = (env.allow_bstat && cfg.bstat != 0 && pa.n_tiles_n == 1 && b_total + 4ll * a_bytes <= budget) ? 1 : 0;
+  const int sub_bytes = a_bytes + (pa.b_stationary ? 0 : b_bytes);
   const int avail = budget - (pa.b_stationary ? (int)b_total : 0);
+  // BK-blocks per stage.  The issue loop and the barrier round trip cost a few hundred cycles per stage whatever the
+  // tile, so a stage should carry ~512 cycles of tensor work: one BK-block is (BK/16) MMAs of BN/2 cycles each.
+  int ksub = cfg.ksub;
+  if (ksub <= 0) {
+    // smallest divisor of the K walk that reaches the target (3 or 9 taps, 2 or 4 channel blocks ...), as long as two
+    // stages of it fit; otherwise the largest divisor that does
+    const int target = std::min(num_k, std::max(1, 512 / ((BK / 16) * (BN / 2))));
+    ksub = 1;
+    for (int d = 1; d <= num_k; ++d) {
+      if (num_k % d != 0 || avail / (d * sub_bytes) < 2) continue;
+      ksub = d;
+      if (d >= target) break;
+    }
+  } else {
+    ksub = std::min(ksub, num_k);
+    while (ksub > 1 && avail / (ksub * sub_bytes) < 2) --ksub;
+  }
+  pa.ksub = ksub;
+  const int stage_bytes = ksub * sub_bytes;
   pa.n_stages = std::min(CONV_TCP_MAX_STAGES, avail / stage_bytes);
   if (pa.n_stages < 2) return fail(YB_ERR_INVALID, "persistent conv: shared memory too small for BN=%d BK=%d", BN, BK);
   const int smem = 1024 + CONV_TCP_HEADER + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0) + (pa.b_stationary ? (int)b_total : 0) +
@@ -383,7 +419,7 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
     YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
     if (env.device < 64) attr_done |= 1ull << env.device;
   }
-  op.launched_stages = pa.n_stages; op.launched_bstat = pa.b_stationary; op.launched_tma_epi = pa.tma_epi;
+  op.launched_stages = pa.n_stages; op.launched_bstat = pa.b_stationary; op.launched_tma_epi = pa.tma_epi; op.launched_ksub = pa.ksub;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = PAIR ? dim3(2 * std::min(pa.n_tiles, env.num_sms / 2)) : dim3(std::min(pa.n_tiles, env.num_sms));
@@ -410,8 +446,12 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
 static int dispatch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const LaunchEnv& env, const ConvCfg& cfg) {
   if (op.cout_pad > CONV_TCP_MAX_COUT_PAD) return fail(YB_ERR_INVALID, "tcgen05 conv supports at most %d output channels", CONV_TCP_MAX_COUT_PAD);
   if (cfg.pair) {
-    if (cfg.bn != 256 || op.bk != 64 || ceil_div(a.M, 128) < 2) return fail(YB_ERR_INVALID, "CTA pairs need BN=256, BK=64 and two M tiles");
-    return launch_conv_tcp<256, 64, true>(st, op, a, env, cfg);
+    if (ceil_div(a.M, 128) < 2) return fail(YB_ERR_INVALID, "CTA pairs need two M tiles");
+#define YB_CASE(BN_, BK_) \
+    if (cfg.bn == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, true>(st, op, a, env, cfg);
+    YB_CASE(256, 64) YB_CASE(128, 64) YB_CASE(64, 64) YB_CASE(128, 32) YB_CASE(64, 32)
+#undef YB_CASE
+    return fail(YB_ERR_INVALID, "no CTA-pair conv instantiation for BN=%d BK=%d", cfg.bn, op.bk);
   }
 #define YB_CASE(BN_, BK_) \
   if (cfg.bn == BN_ && op.bk == BK_) return launch_conv_tcp<BN_, BK_, false>(st, op, a, env, cfg);
@@ -422,12 +462,14 @@ static int dispatch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const L
 }
 
 // Heuristic configuration (used until yb_engine_autotune has measured the alternatives): the widest N tile; CTA pairs
-// (cta_group::2) for the operand-bandwidth-bound layers, i.e. N tile 256 and K >= 512.
+// (cta_group::2) where the mainloop matters: every 3x3 conv (narrow N tiles are MMA-issue bound, wide ones operand-
+// bandwidth bound) and the 1x1 convs with N tile 256 and K >= 512.
 static ConvCfg default_cfg(const Op& op, int max_batch, bool allow_pair) {
   ConvCfg c;
   c.bn = op.bn_max;
   const long long M = (long long)max_batch * op.Ho * op.Wo;
-  c.pair = (allow_pair && c.bn == 256 && op.bk == 64 && op.ksize * op.ksize * op.cin >= 512 && M > 128) ? 1 : 0;
+  const int K = op.ksize * op.ksize * op.cin;
+  c.pair = (allow_pair && c.bn >= 64 && M > 128 && op.bk == 64 && (op.ksize > 1 || (c.bn == 256 && K >= 512))) ? 1 : 0;
   return c;
 }
 
@@ -437,9 +479,9 @@ static std::vector<ConvCfg> candidate_cfgs(const Op& op, int n, bool allow_pair)
   const long long M = (long long)n * op.Ho * op.Wo;
   for (int bn = op.bn_max; bn >= 32 && bn >= op.bn_max / 4; bn >>= 1) {
     for (int pair = 0; pair <= 1; ++pair) {
-      if (pair && !(allow_pair && bn == 256 && op.bk == 64 && M > 128)) continue;
+      if (pair && !(allow_pair && bn >= 64 && M > 128)) continue;
       for (int bstat = 0; bstat <= 1; ++bstat) {
-        if (bstat && (pair || round_up(op.cout, bn) != bn)) continue;
+        if (bstat && round_up(op.cout, bn) != bn) continue;
         for (int te = 0; te <= 1; ++te) {
           if (te && !op.tma_epi) continue;
           ConvCfg c;
@@ -468,7 +510,7 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate};
+      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate, e->dbg_counters};
       ConvCfg cfg = cfg_override ? *cfg_override : op.cfg;
       if (cfg.pair && ceil_div(a.M, 128) < 2) cfg.pair = 0;          // a batch too small to form a pair of M tiles
       YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
@@ -798,6 +840,11 @@ static int build_tensor_maps(yb_engine* e) {
       YB_TRY(make_map_2d(&op.tmOut, view_ptr(e, op.out), rows, op.cout, op.out.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
       if (op.has_res) YB_TRY(make_map_2d(&op.tmRes, view_ptr(e, op.in2), rows, op.cout, op.in2.ld, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
       op.tma_epi = true;
+    } else if (op.out_mode == OUT_PLAIN && op.out.f32 && !op.has_res && op.out.ld % 4 == 0 && op.out.coff == 0) {
+      // fp32 heads: 32 rows x 16 floats per store (the padded channels up to ld are written as well, like the direct path)
+      const long long rows = (long long)e->max_batch * op.Ho * op.Wo;
+      YB_TRY(make_map_2d_f32(&op.tmOut, view_ptr(e, op.out), rows, op.out.ld, op.out.ld, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B));
+      op.tma_epi = true;
     }
   }
   return YB_OK;
@@ -905,17 +952,39 @@ static int autotune(yb_engine* e, int n, int reps) {
         YB_TRY(time_op(e, op, n, &cands[ci], reps, &t));
         ms = std::min(ms, t);
       }
-      snprintf(line, sizeof(line), "%s{\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"stages\": %d, \"ms\": %.5f}", ci ? ", " : "",
-               cands[ci].bn, cands[ci].pair, op.launched_bstat, op.launched_tma_epi, op.launched_stages, ms);
+      snprintf(line, sizeof(line), "%s{\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"stages\": %d, \"ksub\": %d, \"ms\": %.5f}", ci ? ", " : "",
+               cands[ci].bn, cands[ci].pair, op.launched_bstat, op.launched_tma_epi, op.launched_stages, op.launched_ksub, ms);
       js += line;
       if (ms < best) { best = ms; best_cfg = cands[ci]; }
+    }
+    // second pass: BK-blocks per stage for the best configuration found so far
+    {
+      const int num_k = op.ksize * op.ksize * (op.cin / op.bk);
+      const int ks[] = {1, 2, 3, 4, 6, 9};
+      ConvCfg base = best_cfg;
+      for (int k : ks) {
+        if (k > num_k) continue;
+        ConvCfg c = base;
+        c.ksub = k;
+        float ms = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+          float t = 0.f;
+          YB_TRY(time_op(e, op, n, &c, reps, &t));
+          ms = std::min(ms, t);
+        }
+        if (op.launched_ksub != k) continue;            // did not fit: resolved to something already measured
+        snprintf(line, sizeof(line), ", {\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"stages\": %d, \"ksub\": %d, \"ms\": %.5f}",
+                 c.bn, c.pair, op.launched_bstat, op.launched_tma_epi, op.launched_stages, k, ms);
+        js += line;
+        if (ms < best) { best = ms; best_cfg = c; }
+      }
     }
     // keep the heuristic unless a candidate is measurably (>1.5%) faster: avoids flapping on noise
     float def_best = def_ms;
     for (int rep = 0; rep < 2; ++rep) { float t = 0.f; YB_TRY(time_op(e, op, n, &def, reps, &t)); def_best = std::min(def_best, t); }
     if (best > def_best * 0.985f) { best_cfg = def; best = def_best; }
-    snprintf(line, sizeof(line), "], \"chosen\": {\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"ms\": %.5f}}", best_cfg.bn, best_cfg.pair,
-             best_cfg.bstat, best_cfg.tma_epi, best);
+    snprintf(line, sizeof(line), "], \"chosen\": {\"bn\": %d, \"pair\": %d, \"bstat\": %d, \"tma_epi\": %d, \"ksub\": %d, \"ms\": %.5f}}", best_cfg.bn, best_cfg.pair,
+             best_cfg.bstat, best_cfg.tma_epi, best_cfg.ksub, best);
     js += line;
     op.cfg = best_cfg; op.tuned_ms = best; op.default_ms = def_best;
     Done d;
@@ -1006,6 +1075,7 @@ void yb_engine_destroy(yb_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (Op& op : e->ops) { cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift); }
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  cudaFree(e->dbg_counters);
   cudaFree(e->arena); cudaFree(e->input_dev[0]); cudaFree(e->input_dev[1]); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
   e->post.release();
   for (int i = 0; i < 2; ++i) {
@@ -1267,6 +1337,17 @@ int yb_engine_set_option(yb_engine* e, const char* name, int value) {
   if (!e || !name) return fail(YB_ERR_INVALID, "yb_engine_set_option: bad argument");
   if (!strcmp(name, "pdl")) e->pdl = value != 0;
   else if (!strcmp(name, "ablate")) e->ablate = value & 15;
+  else if (!strcmp(name, "cycles")) {       // in-kernel cycle counters of the conv roles (read with yb_engine_read_cycles)
+    YB_TRY(set_device(e->device));
+    if (value && !e->dbg_counters) {
+      YB_CUDA(cudaMalloc(&e->dbg_counters, 16 * sizeof(unsigned long long)));
+      YB_CUDA(cudaMemset(e->dbg_counters, 0, 16 * sizeof(unsigned long long)));
+    } else if (!value && e->dbg_counters) {
+      YB_CUDA(cudaStreamSynchronize(e->stream));
+      cudaFree(e->dbg_counters);
+      e->dbg_counters = nullptr;
+    }
+  }
   else if (!strcmp(name, "bstat")) e->b_stationary = value != 0;
   else if (!strcmp(name, "tma_epi")) e->tma_epilogue = value != 0;
   else if (!strcmp(name, "pairs")) {
@@ -1276,14 +1357,25 @@ int yb_engine_set_option(yb_engine* e, const char* name, int value) {
   return YB_OK;
 }
 
-int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi) {
+int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bstat, int tma_epi, int ksub) {
   if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_set_conv_cfg: bad argument");
   Op& op = e->ops[op_index];
   if (op.kind != OP_CONV || op.path != PATH_TC) return fail(YB_ERR_INVALID, "op %d is not a tcgen05 conv", op_index);
   if (bn == 0) { op.cfg = default_cfg(op, e->max_batch, e->cta_pairs); return YB_OK; }
   if ((bn != 32 && bn != 64 && bn != 128 && bn != 256) || bn > op.bn_max) return fail(YB_ERR_INVALID, "op %d: N tile %d not available (max %d)", op_index, bn, op.bn_max);
-  if (pair && (bn != 256 || op.bk != 64)) return fail(YB_ERR_INVALID, "op %d: CTA pairs need BN=256 and BK=64", op_index);
-  op.cfg.bn = bn; op.cfg.pair = pair ? 1 : 0; op.cfg.bstat = bstat; op.cfg.tma_epi = tma_epi;
+  if (pair && bn < 64) return fail(YB_ERR_INVALID, "op %d: CTA pairs need an N tile of at least 64", op_index);
+  if (ksub < 0 || ksub > 64) return fail(YB_ERR_INVALID, "op %d: bad blocks-per-stage %d", op_index, ksub);
+  op.cfg.bn = bn; op.cfg.pair = pair ? 1 : 0; op.cfg.bstat = bstat; op.cfg.tma_epi = tma_epi; op.cfg.ksub = ksub;
+  return YB_OK;
+}
+
+int yb_engine_read_cycles(yb_engine* e, unsigned long long* out16, int reset) {
+  if (!e || !out16) return fail(YB_ERR_INVALID, "yb_engine_read_cycles: bad argument");
+  if (!e->dbg_counters) return fail(YB_ERR_STATE, "cycle counters are off: yb_engine_set_option(e, \"cycles\", 1) first");
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  YB_CUDA(cudaMemcpy(out16, e->dbg_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) YB_CUDA(cudaMemset(e->dbg_counters, 0, 16 * sizeof(unsigned long long)));
   return YB_OK;
 }
 
@@ -1383,7 +1475,7 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   return YB_OK;
 }
 
-int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages) {
+int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages, int* ksub) {
   if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_op_cfg: bad argument");
   const Op& op = e->ops[op_index];
   if (bn) *bn = op.cfg.bn;
@@ -1391,6 +1483,7 @@ int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat,
   if (bstat) *bstat = op.launched_bstat;
   if (tma_epi) *tma_epi = op.launched_tma_epi;
   if (stages) *stages = op.launched_stages;
+  if (ksub) *ksub = op.launched_ksub;
   return YB_OK;
 }
 

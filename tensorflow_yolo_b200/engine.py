@@ -152,9 +152,9 @@ class Engine(object):
                 "flops_per_image": fl.value}
 
     def op_cfg(self, op_index):
-        v = [ctypes.c_int() for _ in range(5)]
+        v = [ctypes.c_int() for _ in range(6)]
         _lib.check(_lib.lib().yb_engine_op_cfg(self._h, op_index, *[ctypes.byref(x) for x in v]))
-        return dict(zip(("bn", "pair", "bstat", "tma_epi", "stages"), [x.value for x in v]))
+        return dict(zip(("bn", "pair", "bstat", "tma_epi", "stages", "ksub"), [x.value for x in v]))
 
     def set_conv_impl(self, impl):
         _lib.check(_lib.lib().yb_engine_set_conv_impl(self._h, impl))
@@ -177,14 +177,23 @@ class Engine(object):
     def set_option(self, name, value):
         _lib.check(_lib.lib().yb_engine_set_option(self._h, name.encode("ascii"), int(value)))
 
-    def set_conv_cfg(self, op_index, bn, pair=0, bstat=-1, tma_epi=-1):
-        _lib.check(_lib.lib().yb_engine_set_conv_cfg(self._h, op_index, bn, pair, bstat, tma_epi))
+    def set_conv_cfg(self, op_index, bn, pair=0, bstat=-1, tma_epi=-1, ksub=0):
+        _lib.check(_lib.lib().yb_engine_set_conv_cfg(self._h, op_index, bn, pair, bstat, tma_epi, ksub))
 
     def time_op(self, op_index, n=None, reps=10):
         ms = ctypes.c_float()
         _lib.check(_lib.lib().yb_engine_time_op(self._h, op_index, int(n or self.max_batch), reps, ctypes.byref(ms)))
         self.last_n = 0
         return ms.value
+
+    CYCLE_NAMES = ("prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_tmem", "mma_total", "epi_wait_acc",
+                   "epi_wait_res", "epi_wait_buf", "epi_tmem_ld", "epi_math", "epi_total", "epi_fence_store")
+
+    def read_cycles(self, reset=True):
+        """In-kernel cycle counters of the conv roles (set_option("cycles", 1) first), summed over CTAs and launches."""
+        out = np.zeros(16, dtype=np.uint64)
+        _lib.check(_lib.lib().yb_engine_read_cycles(self._h, out.ctypes.data, int(reset)))
+        return dict(zip(self.CYCLE_NAMES, [int(v) for v in out]))
 
     def launch_count(self):
         a, b = ctypes.c_int(), ctypes.c_int()

@@ -182,13 +182,13 @@ def test_autotune_keeps_results_bit_identical():
         for bn in (32, 64, 128, 256):
             for pair in (0, 1):
                 for bstat in (0, 1):
-                    for te in (0, 1):
+                    for te, ksub in ((0, 0), (1, 0), (1, 1), (0, 2), (1, 3), (1, 9)):
                         try:
-                            eng.set_conv_cfg(op_i, bn, pair, bstat, te)
+                            eng.set_conv_cfg(op_i, bn, pair, bstat, te, ksub)
                         except Exception:
                             continue          # not available for this layer (N tile wider than Cout, pair without BN=256)
                         eng.forward(x)
-                        assert np.array_equal(eng.read_output(), y0), (op_i, bn, pair, bstat, te)
+                        assert np.array_equal(eng.read_output(), y0), (op_i, bn, pair, bstat, te, ksub)
         eng.set_conv_cfg(op_i, 0)
     with pytest.raises(Exception):
         eng.set_option("no_such_option", 1)

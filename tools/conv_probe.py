@@ -76,17 +76,49 @@ def main():
             eng.set_option("ablate", mask)
             row[name] = eng.time_op(op_i, B, args.reps)
         eng.set_option("ablate", 0)
+        # in-kernel cycle counters: which role waits on which (full kernel, and the epilogue running alone)
+        eng.set_option("cycles", 1)
+        for tag, mask in (("roles", 0), ("roles_epi_only", 14)):
+            eng.set_option("ablate", mask)
+            eng.read_cycles(reset=True)
+            eng.time_op(op_i, B, args.reps)
+            cyc = eng.read_cycles(reset=True)
+            pt, mt, et = max(cyc["prod_total"], 1), max(cyc["mma_total"], 1), max(cyc["epi_total"], 1)
+            row[tag] = {"prod_wait_empty": cyc["prod_wait_empty"] / pt, "mma_wait_full": cyc["mma_wait_full"] / mt,
+                        "mma_wait_tmem": cyc["mma_wait_tmem"] / mt, "epi_wait_acc": cyc["epi_wait_acc"] / et,
+                        "epi_wait_res": cyc["epi_wait_res"] / et, "epi_wait_buf": cyc["epi_wait_buf"] / et,
+                        "epi_tmem_ld": cyc["epi_tmem_ld"] / et, "epi_math": cyc["epi_math"] / et,
+                        "epi_fence_store": cyc["epi_fence_store"] / et}
+        eng.set_option("ablate", 0)
+        eng.set_option("cycles", 0)
         row["cfg"] = eng.op_cfg(op_i)
         row["tflops"] = row["gflop"] / row["full"] if row["full"] > 0 else 0.0
         table.append(row)
         print("op {:3d} {:>16s} k{} s{} cin{:4d} cfg {} | ".format(op_i, str(tuple(spec.shape)), spec.ksize, spec.stride, cin, row["cfg"]) +
               " ".join("{}={:.3f}".format(n, row[n]) for n, _ in ABLATIONS) + " | {:.0f} TF".format(row["gflop"] / row["full"]), flush=True)
+        print("        roles: " + " ".join("{}={:.0%}".format(k, v) for k, v in row["roles"].items()), flush=True)
+        print("        epi_only roles: " + " ".join("{}={:.0%}".format(k, v) for k, v in row["roles_epi_only"].items() if k.startswith("epi")), flush=True)
     result["ablation"] = table
 
     # ---- autotune ----
     eng.forward(x)
     report = eng.autotune(B, reps=5)
     result["tune"] = report
+    # interleaved A/B (power/thermal drift moves single measurements by a few percent): tuned vs heuristic, PDL on
+    eng.forward(x)
+    eng.sync()
+    tuned_cfg = {o: eng.op_cfg(o) for o in range(n_ops) if eng.op_info(o)["path"] == 0}
+    ab = {"tuned": [], "heuristic": []}
+    for _ in range(4):
+        for o, c in tuned_cfg.items():
+            eng.set_conv_cfg(o, c["bn"], c["pair"], c["bstat"], c["tma_epi"], c["ksub"])
+        ab["tuned"].append(forward_ms(eng, x))
+        for o in tuned_cfg:
+            eng.set_conv_cfg(o, 0)
+        ab["heuristic"].append(forward_ms(eng, x))
+    result["forward_ms_ab"] = ab
+    for o, c in tuned_cfg.items():
+        eng.set_conv_cfg(o, c["bn"], c["pair"], c["bstat"], c["tma_epi"], c["ksub"])
     result["forward_ms_tuned_pdl"] = forward_ms(eng, x)
     eng.set_option("pdl", 0)
     result["forward_ms_tuned_nopdl"] = forward_ms(eng, x)
@@ -95,8 +127,8 @@ def main():
         best = min(o["candidates"], key=lambda c: c["ms"])
         print("tune op {:3d} cin{:4d} cout{:4d} k{} s{} {}x{} default {:.4f} best {:.4f} {} chosen {}".format(
             o["op"], o["cin"], o["cout"], o["k"], o["stride"], o["ho"], o["wo"], o["default_ms"], best["ms"],
-            {k: best[k] for k in ("bn", "pair", "bstat", "tma_epi", "stages")}, o["chosen"]), flush=True)
-    print({k: v for k, v in result.items() if k.startswith("forward_ms")})
+            {k: best[k] for k in ("bn", "pair", "bstat", "tma_epi", "stages", "ksub")}, o["chosen"]), flush=True)
+    print({k: v for k, v in result.items() if k.startswith("forward_ms")}, flush=True)
     with open(args.out, "w") as f:
         json.dump(result, f, indent=0)
 
