@@ -96,6 +96,12 @@ const char* yb_last_error(void);
 /* number of visible CUDA devices (0 and YB_OK when there is no GPU / no driver) */
 int yb_device_count(int* count);
 
+/* CRC-32C (Castagnoli) of data[0..n) continuing from `seed` (0 = fresh), the checksum TensorFlow's tensor-bundle
+ * checkpoints carry per tensor and per index block (tensorflow/core/lib/hash/crc32c.h); used by the checkpoint
+ * reader that replaces tf.train.Saver.restore (net/yolo.py:71-72, net/base.py:55-61).  Host only.
+ * impl 0 = SSE4.2 when available, 1 = portable tables. */
+int yb_crc32c(const void* data, size_t n, uint32_t seed, int impl, uint32_t* out);
+
 /* ---- engine: replaces tf graph build + tf.Session (net/yolo.py:63,67-68) ---- */
 /* plan: the flat layer list.  decode_mode/num_classes describe the head.  For YOLOv2 (whose
  * reference plan ends in the linear conv, net/v2.py:52-59) the caller appends one YB_YOLO entry

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "yb_abi_version": (ctypes.c_int, []),
     "yb_last_error": (ctypes.c_char_p, []),
     "yb_device_count": (ctypes.c_int, [_P(ctypes.c_int)]),
+    "yb_crc32c": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, _P(ctypes.c_uint32)]),
     "yb_engine_create": (ctypes.c_int, [_P(_plan.yb_layer), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P(ctypes.c_void_p)]),
     "yb_engine_destroy": (None, [ctypes.c_void_p]),
@@ -116,6 +117,15 @@ def lib():
 def check(code):
     if code != YB_OK:
         raise YoloB200Error(code, lib().yb_last_error().decode("utf-8", "replace"))
+
+
+def crc32c(data, seed=0, impl=0):
+    """CRC-32C of a bytes-like object / contiguous numpy array (native, SSE4.2 when available)."""
+    import numpy as np
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    out = ctypes.c_uint32(0)
+    check(lib().yb_crc32c(buf.ctypes.data if buf.size else None, buf.size, seed, impl, ctypes.byref(out)))
+    return out.value
 
 
 def device_count():

@@ -1003,6 +1003,55 @@ static int autotune(yb_engine* e, int n, int reps) {
 // ================================================================================================
 extern "C" {
 
+// ---- CRC-32C (Castagnoli), the checksum of TensorFlow's tensor-bundle checkpoints (host only, no GPU needed) ----
+static uint32_t g_crc_table[8][256];
+static bool g_crc_ready = false;
+static void crc32c_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_table[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xFFu];
+  g_crc_ready = true;
+}
+#if defined(__x86_64__)
+__attribute__((target("sse4.2"))) static uint32_t crc32c_hw(uint32_t crc, const unsigned char* p, size_t n) {
+  uint64_t c = crc;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7u)) { c = __builtin_ia32_crc32qi((uint32_t)c, *p++); --n; }
+  while (n >= 8) { uint64_t v; memcpy(&v, p, 8); c = __builtin_ia32_crc32di(c, v); p += 8; n -= 8; }
+  while (n) { c = __builtin_ia32_crc32qi((uint32_t)c, *p++); --n; }
+  return (uint32_t)c;
+}
+#endif
+static uint32_t crc32c_sw(uint32_t crc, const unsigned char* p, size_t n) {   // slicing-by-8
+  if (!g_crc_ready) crc32c_init();
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+    lo ^= crc;
+    crc = g_crc_table[7][lo & 0xFF] ^ g_crc_table[6][(lo >> 8) & 0xFF] ^ g_crc_table[5][(lo >> 16) & 0xFF] ^ g_crc_table[4][lo >> 24] ^
+          g_crc_table[3][hi & 0xFF] ^ g_crc_table[2][(hi >> 8) & 0xFF] ^ g_crc_table[1][(hi >> 16) & 0xFF] ^ g_crc_table[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) crc = (crc >> 8) ^ g_crc_table[0][(crc ^ *p++) & 0xFFu];
+  return crc;
+}
+
+// CRC-32C of data[0..n) continuing from `seed` (0 for a fresh checksum), as crc32c::Extend in TensorFlow/LevelDB.
+// impl: 0 = fastest available (SSE4.2 when the CPU has it), 1 = portable table version (used to cross-check).
+int yb_crc32c(const void* data, size_t n, uint32_t seed, int impl, uint32_t* out) {
+  if ((!data && n) || !out) return fail(YB_ERR_INVALID, "yb_crc32c: bad argument");
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = seed ^ 0xFFFFFFFFu;
+#if defined(__x86_64__)
+  if (impl == 0 && __builtin_cpu_supports("sse4.2")) { *out = crc32c_hw(c, p, n) ^ 0xFFFFFFFFu; return YB_OK; }
+#endif
+  *out = crc32c_sw(c, p, n) ^ 0xFFFFFFFFu;
+  return YB_OK;
+}
+
 int yb_abi_version(void) { return YB_ABI_VERSION; }
 const char* yb_last_error(void) { return g_err; }
 

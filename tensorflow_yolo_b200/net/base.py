@@ -149,12 +149,41 @@ class Session(object):
         return out
 
 
+class Saver(object):
+    """Stand-in for tf.train.Saver on the TEST path (net/yolo.py:71): restore() reads a TensorFlow tensor-bundle
+    checkpoint without TensorFlow (tensorflow_yolo_b200.checkpoint) and uploads it to the engine; save() writes the
+    network's variables back in the same layout."""
+
+    def restore(self, sess, save_path):
+        from .. import checkpoint
+        layers = sess.layers
+        if layers is None:
+            raise ValueError("Session was created without a layer list")
+        stream = checkpoint.stream_from_checkpoint(layers, save_path)
+        state = state_of(layers)
+        need = _plan.weight_count(state.graph.specs)
+        if stream.size != need:
+            raise ValueError("checkpoint yields {} weight values, the network needs {}".format(stream.size, need))
+        _AssignWeights(state, stream, need).run()
+
+    def save(self, sess, save_path):
+        from .. import checkpoint
+        state = state_of(sess.layers)
+        if state.pending_stream is None:
+            raise ValueError("no weights have been loaded into this network")
+        checkpoint.checkpoint_from_stream(sess.layers, state.pending_stream, save_path)
+        return save_path
+
+
 def load_checkpoint_by_path(saver, sess, checkpoint_path):
-    """TF tensor-bundle checkpoints are not readable without TensorFlow yet; behave like
-    the reference's failure branch (net/base.py:55-61): report and return False so the caller falls back
-    to the darknet .weights file."""
-    print("Failed to load {}: TensorFlow checkpoints are not supported by tensorflow_yolo_b200".format(checkpoint_path))
-    return False
+    """Same contract as the reference (net/base.py:55-61): True when the checkpoint was restored, otherwise the
+    reason is printed and False tells the caller to fall back to the darknet .weights file."""
+    try:
+        (saver if saver is not None else Saver()).restore(sess, checkpoint_path)
+        return True
+    except Exception as e:
+        print("Failed to load {}: {}".format(checkpoint_path, str(e)))
+        return False
 
 
 def load_image_paths(path_to_img_dir):

@@ -45,7 +45,8 @@ class Yolo(object):
         base.state_of(net).ensure_engine(batch_size)
         results = {}
         with base.Session(net) as sess:
-            if not base.load_checkpoint_by_path(None, sess, checkpoint_path):
+            saver = base.Saver()
+            if not base.load_checkpoint_by_path(saver, sess, checkpoint_path):
                 sess.run(self.load_weights(net, pretrained_weights_path))
                 print("Pre-trained weights loaded.")
             else:

@@ -66,3 +66,28 @@ def test_launcher_test_mode(tmp_path, version, capsys):
                 d = np.abs(ref_xy - np.asarray([b.x, b.y])).max(1)
                 hits += bool(d.min() < 0.02)
             assert hits >= 0.7 * len(boxes)
+
+
+def test_checkpoint_is_tried_first_and_gives_the_same_detections(tmp_path, capsys):
+    """net/yolo.py:71-78: a readable checkpoint_path wins over pretrained_weights_path; the detections are those of
+    the .weights run bit for bit (both sources reach the engine as the same float stream)."""
+    import launcher
+    from tensorflow_yolo_b200 import checkpoint as ckpt
+    shape = (128, 128, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=2, obj_bias=-1.0)
+    ini = _write_case(tmp_path, "v3", shape, 80, helpers.V3_ANCHORS, stream)
+    from_weights = launcher._main(launcher.load_config(ini), "test")
+    assert "Pre-trained weights loaded." in capsys.readouterr().out
+    ckpt.checkpoint_from_stream(net, stream, str(tmp_path / "ckpt" / "yolo.ckpt"), extra={"global_step": np.asarray(3, np.int64)})
+    os.remove(str(tmp_path / "bin" / "net.weights"))            # the .weights file must not be needed any more
+    text = open(ini).read().replace("checkpoint_path = ../nope", "checkpoint_path = ../ckpt/yolo.ckpt")
+    open(ini, "w").write(text)
+    from_ckpt = launcher._main(launcher.load_config(ini), "test")
+    out = capsys.readouterr().out
+    assert "restored." in out and "Pre-trained weights loaded." not in out
+    assert sorted(from_ckpt) == sorted(from_weights)
+    for path in from_weights:
+        a, b = from_weights[path], from_ckpt[path]
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert (x.x, x.y, x.w, x.h, x.prob, x.class_idx) == (y.x, y.y, y.w, y.h, y.prob, y.class_idx)
