@@ -123,6 +123,20 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
  * results stay on the device. */
 int yb_engine_forward(yb_engine* e, const void* images, int dtype, int mem, int n);
 
+/* Replaces base.generate_test_batch / preprocess_image (net/base.py:115-168) + the forward: takes the decoded 8-bit
+ * BGR images as cv2.imread returns them (host memory, any sizes; strides[i] = bytes per row, NULL = widths[i]*3),
+ * and does cv2.resize(image, (input_h, input_w)) [INTER_LINEAR, bit-exact fixed point], BGR->RGB and the /255 scaling
+ * on the device before running the conv stack.  The raw images are uploaded on a copy stream into double-buffered
+ * staging, so the upload of batch i+1 overlaps the compute of batch i.  Like the reference, only square network
+ * inputs work (its dsize = (input_h, input_w) quirk makes its own placeholder reject anything else). */
+int yb_engine_forward_raw(yb_engine* e, const void* const* images, const int* heights, const int* widths,
+                          const int* strides, int n);
+/* The preprocessed uint8 RGB batch [n, H, W, 3] of the last yb_engine_forward_raw (parity tests). */
+int yb_engine_read_input_u8(yb_engine* e, unsigned char* host_out, size_t capacity);
+/* Stand-alone cv2.resize(image, (dst_w, dst_h)) + BGR->RGB of n host images into host memory [n, dst_h, dst_w, 3]. */
+int yb_resize_bgr2rgb(const void* const* images, const int* heights, const int* widths, const int* strides, int n,
+                      int dst_h, int dst_w, unsigned char* dst_host, int device);
+
 /* Copies the reference's net[-1].out for the last forward to host float32:
  * [n, R, 5+C] (v3, net/v3.py:90-93) or [n, h, w, A*(5+C)] (v2, net/v2.py:59).  For parity tests;
  * the detect path never materialises it.  capacity in floats. */

@@ -1,4 +1,4 @@
-"""CLI with the reference's flags (launcher.py): --config <ini> --mode test.  train/anchor are out of scope."""
+"""CLI with the reference's flags (launcher.py): --config <ini> --mode test|anchor.  train is out of scope."""
 import argparse
 import ast
 import configparser
@@ -34,8 +34,15 @@ def _main(cfg, mode, test_section="TEST"):
         raise ValueError("Unsupported version: {}".format(version))
     if mode == "test":
         return yolo.test({**cfg[test_section], **cfg["COMMON"]})
-    if mode in ("train", "anchor"):
-        raise ValueError("mode '{}' is not implemented by tensorflow_yolo_b200 (TEST path only)".format(mode))
+    if mode == "anchor":
+        anchors, class_names = yolo.generate_anchors({**cfg["ANCHOR"], **cfg["COMMON"]})
+        print("Anchors: ")
+        print("\t{}".format(anchors))
+        print("Class names: ")
+        print("\t{}".format(class_names))
+        return anchors, class_names
+    if mode == "train":
+        raise ValueError("mode 'train' is not implemented by tensorflow_yolo_b200 (TEST and ANCHOR paths only)")
     raise ValueError("Unsupported mode: {}".format(mode))
 
 
@@ -43,7 +50,7 @@ if __name__ == "__main__":
     args = argparse.ArgumentParser()
     args.add_argument("--config", dest="config", help="Path to configuration file",
                       default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "config", "yolo_3.ini"))
-    args.add_argument("--mode", dest="mode", help="Mode: (test)", default="test")
+    args.add_argument("--mode", dest="mode", help="Mode: (test|anchor)", default="test")
     args.add_argument("--section", dest="section", help="ini section holding the TEST parameters", default="TEST")
     c = args.parse_args()
     _main(load_config(c.config), c.mode.lower(), c.section)

@@ -47,6 +47,11 @@ _SIGNATURES = {
     "yb_engine_destroy": (None, [ctypes.c_void_p]),
     "yb_engine_load_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _P(ctypes.c_size_t)]),
     "yb_engine_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "yb_engine_forward_raw": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_void_p), _P(ctypes.c_int), _P(ctypes.c_int),
+                                             _P(ctypes.c_int), ctypes.c_int]),
+    "yb_engine_read_input_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "yb_resize_bgr2rgb": (ctypes.c_int, [_P(ctypes.c_void_p), _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_int), ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_read_output": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
     "yb_engine_output_shape": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int), _P(ctypes.c_int)]),
     "yb_engine_read_layer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,

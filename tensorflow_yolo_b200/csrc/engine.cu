@@ -21,6 +21,7 @@
 #include "aux_kernels.cuh"
 #include "conv_tc.cuh"
 #include "post.cuh"
+#include "preprocess.cuh"
 
 namespace yb {
 
@@ -302,6 +303,112 @@ struct Head {
 
 }  // namespace yb
 
+// ------------------------------------------------------------------------------------------------
+// device-side image preprocessing (cv2.resize INTER_LINEAR + BGR->RGB), shared by the engine and yb_resize_bgr2rgb
+// ------------------------------------------------------------------------------------------------
+namespace yb {
+
+// cv2's coefficient tables (modules/imgproc/src/resize.cpp, cv::resize -> resizeGeneric_ for CV_8U INTER_LINEAR),
+// computed in the same types: double scale, float fraction, short weights with 11 fractional bits.
+static void build_resize_table(int src, int dst, bool clamp_weights, std::vector<ResizeTab>& out) {
+  const double inv_scale = (double)dst / (double)src;
+  const double scale = 1. / inv_scale;
+  for (int d = 0; d < dst; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= (float)s;
+    if (clamp_weights) {                      // columns only: the row index is clamped where it is used instead
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    ResizeTab t;
+    t.ofs = s;
+    t.c0 = (short)std::lrintf((1.f - f) * 2048.f);      // cvRound: round half to even
+    t.c1 = (short)std::lrintf(f * 2048.f);
+    out.push_back(t);
+  }
+}
+
+struct PreCtx {
+  unsigned char* raw[2] = {nullptr, nullptr};     // device copies of the caller's images (double-buffered)
+  size_t raw_cap[2] = {0, 0};
+  ResizeImage* d_imgs[2] = {nullptr, nullptr};
+  ResizeTab* d_tabs[2] = {nullptr, nullptr};
+  size_t imgs_cap[2] = {0, 0}, tabs_cap[2] = {0, 0};
+  std::vector<unsigned char> pinned_dummy;
+
+  void release() {
+    for (int i = 0; i < 2; ++i) { cudaFree(raw[i]); cudaFree(d_imgs[i]); cudaFree(d_tabs[i]); raw[i] = nullptr; d_imgs[i] = nullptr; d_tabs[i] = nullptr; raw_cap[i] = imgs_cap[i] = tabs_cap[i] = 0; }
+  }
+
+  // Uploads n BGR images (host memory) on copy stream `cs`, builds their tables and enqueues the resize kernel on `ks`
+  // after the copies (event `ev`).  dst: device [n, dh, dw, 3] uint8 RGB.
+  int run(int slot, cudaStream_t cs, cudaStream_t ks, cudaEvent_t ev, const void* const* images, const int* heights, const int* widths,
+          const int* strides, int n, int dh, int dw, unsigned char* dst) {
+    size_t total = 0;
+    std::vector<size_t> offs(n);
+    for (int i = 0; i < n; ++i) {
+      if (!images[i] || heights[i] <= 0 || widths[i] <= 0) return fail(YB_ERR_INVALID, "image %d: bad pointer or size", i);
+      const int stride = strides ? strides[i] : widths[i] * 3;
+      if (stride < widths[i] * 3) return fail(YB_ERR_INVALID, "image %d: row stride %d smaller than %d", i, stride, widths[i] * 3);
+      offs[i] = total;
+      total += ((size_t)heights[i] * stride + 255) & ~(size_t)255;
+    }
+    if (total > raw_cap[slot]) {
+      YB_CUDA(cudaStreamSynchronize(ks));
+      cudaFree(raw[slot]); raw[slot] = nullptr; raw_cap[slot] = 0;
+      YB_CUDA(cudaMalloc(&raw[slot], total + total / 4));
+      raw_cap[slot] = total + total / 4;
+    }
+    std::vector<ResizeImage> imgs(n);
+    std::vector<ResizeTab> tabs;
+    struct Key { int sh, sw, xtab, ytab; };
+    std::vector<Key> seen;
+    for (int i = 0; i < n; ++i) {
+      const int stride = strides ? strides[i] : widths[i] * 3;
+      YB_CUDA(cudaMemcpyAsync(raw[slot] + offs[i], images[i], (size_t)heights[i] * stride, cudaMemcpyHostToDevice, cs));
+      ResizeImage& im = imgs[i];
+      im.src = raw[slot] + offs[i]; im.sh = heights[i]; im.sw = widths[i]; im.stride = stride;
+      im.area2x = (widths[i] == 2 * dw && heights[i] == 2 * dh) ? 1 : 0;
+      im.xtab = im.ytab = 0;
+      if (im.area2x) continue;
+      const Key* hit = nullptr;
+      for (const Key& k : seen) if (k.sh == im.sh && k.sw == im.sw) { hit = &k; break; }
+      if (hit) { im.xtab = hit->xtab; im.ytab = hit->ytab; continue; }
+      im.xtab = (int)tabs.size();
+      build_resize_table(im.sw, dw, true, tabs);
+      im.ytab = (int)tabs.size();
+      build_resize_table(im.sh, dh, false, tabs);
+      seen.push_back(Key{im.sh, im.sw, im.xtab, im.ytab});
+    }
+    if (tabs.empty()) tabs.push_back(ResizeTab{0, 0, 0});
+    if ((size_t)n > imgs_cap[slot]) {
+      YB_CUDA(cudaStreamSynchronize(ks));
+      cudaFree(d_imgs[slot]); d_imgs[slot] = nullptr;
+      YB_CUDA(cudaMalloc(&d_imgs[slot], (size_t)n * sizeof(ResizeImage)));
+      imgs_cap[slot] = n;
+    }
+    if (tabs.size() > tabs_cap[slot]) {
+      YB_CUDA(cudaStreamSynchronize(ks));
+      cudaFree(d_tabs[slot]); d_tabs[slot] = nullptr;
+      YB_CUDA(cudaMalloc(&d_tabs[slot], tabs.size() * 2 * sizeof(ResizeTab)));
+      tabs_cap[slot] = tabs.size() * 2;
+    }
+    // descriptors and tables are small: synchronous copies from these temporaries on the copy stream
+    YB_CUDA(cudaMemcpyAsync(d_imgs[slot], imgs.data(), (size_t)n * sizeof(ResizeImage), cudaMemcpyHostToDevice, cs));
+    YB_CUDA(cudaMemcpyAsync(d_tabs[slot], tabs.data(), tabs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, cs));
+    YB_CUDA(cudaStreamSynchronize(cs));          // the host vectors die at return; pageable copies have completed anyway
+    YB_CUDA(cudaEventRecord(ev, cs));
+    YB_CUDA(cudaStreamWaitEvent(ks, ev, 0));
+    dim3 grid(ceil_div(dw, 128), dh, n);
+    resize_bgr2rgb_kernel<<<grid, 128, 0, ks>>>(d_imgs[slot], d_tabs[slot], dh, dw, dst);
+    YB_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
+};
+
+}  // namespace yb
+
 using namespace yb;
 
 struct yb_engine {
@@ -342,6 +449,8 @@ struct yb_engine {
   float* scratch_f32 = nullptr;   // read_output / read_layer staging
   size_t scratch_floats = 0;
   PostCtx post;
+  PreCtx pre;
+  bool last_input_is_u8_staged = false;      // the last forward's input sits in input_dev[] as uint8 (forward_raw)
   bool weights_loaded = false;
   int last_n = 0;
   bool detected = false;
@@ -1127,6 +1236,7 @@ void yb_engine_destroy(yb_engine* e) {
   cudaFree(e->dbg_counters);
   cudaFree(e->arena); cudaFree(e->input_dev[0]); cudaFree(e->input_dev[1]); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
   e->post.release();
+  e->pre.release();
   for (int i = 0; i < 2; ++i) {
     if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
     if (e->ev_input_free[i]) cudaEventDestroy(e->ev_input_free[i]);
@@ -1199,28 +1309,8 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
   return YB_OK;
 }
 
-static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, int n, cudaEvent_t* evs, int* n_ev) {
-  if (!e || !images) return fail(YB_ERR_INVALID, "yb_engine_forward: bad argument");
-  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
-  if (dtype != YB_F32 && dtype != YB_U8) return fail(YB_ERR_INVALID, "unknown image dtype %d", dtype);
-  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_forward before yb_engine_load_weights");
-  YB_TRY(set_device(e->device));
-  const size_t bytes = (size_t)n * e->H * e->W * e->C * (dtype == YB_F32 ? 4 : 1);
-  int slot = -1;
-  if (mem == YB_MEM_HOST) {
-    // staging[slot] may still be read by the first conv of the forward before last: wait for it, copy on the
-    // copy stream (overlaps whatever the compute stream is doing), then make the compute stream wait for the copy
-    slot = e->stage_toggle;
-    e->stage_toggle ^= 1;
-    YB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_input_free[slot], 0));
-    YB_CUDA(cudaMemcpyAsync(e->input_dev[slot], images, bytes, cudaMemcpyHostToDevice, e->copy_stream));
-    YB_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
-    YB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
-    e->cur_input = e->input_dev[slot];
-  } else {
-    e->cur_input = images;
-  }
-  e->cur_input_dtype = dtype;
+// enqueues every op of the plan on the engine's stream; slot >= 0: the input sits in staging buffer `slot`
+static int enqueue_ops(yb_engine* e, int n, int slot, cudaEvent_t* evs, int* n_ev) {
   e->fwd_launches = 0;
   std::vector<cudaEvent_t> own;
   if (!evs && e->prof_on) {
@@ -1243,8 +1333,97 @@ static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, in
   return YB_OK;
 }
 
+static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, int n, cudaEvent_t* evs, int* n_ev) {
+  if (!e || !images) return fail(YB_ERR_INVALID, "yb_engine_forward: bad argument");
+  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
+  if (dtype != YB_F32 && dtype != YB_U8) return fail(YB_ERR_INVALID, "unknown image dtype %d", dtype);
+  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_forward before yb_engine_load_weights");
+  YB_TRY(set_device(e->device));
+  const size_t bytes = (size_t)n * e->H * e->W * e->C * (dtype == YB_F32 ? 4 : 1);
+  int slot = -1;
+  if (mem == YB_MEM_HOST) {
+    // staging[slot] may still be read by the first conv of the forward before last: wait for it, copy on the
+    // copy stream (overlaps whatever the compute stream is doing), then make the compute stream wait for the copy
+    slot = e->stage_toggle;
+    e->stage_toggle ^= 1;
+    YB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_input_free[slot], 0));
+    YB_CUDA(cudaMemcpyAsync(e->input_dev[slot], images, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    YB_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+    YB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    e->cur_input = e->input_dev[slot];
+  } else {
+    e->cur_input = images;
+  }
+  e->cur_input_dtype = dtype;
+  e->last_input_is_u8_staged = false;
+  return enqueue_ops(e, n, slot, evs, n_ev);
+}
+
 int yb_engine_forward(yb_engine* e, const void* images, int dtype, int mem, int n) {
   return forward_impl(e, images, dtype, mem, n, nullptr, nullptr);
+}
+
+int yb_engine_forward_raw(yb_engine* e, const void* const* images, const int* heights, const int* widths, const int* strides, int n) {
+  if (!e || !images || !heights || !widths) return fail(YB_ERR_INVALID, "yb_engine_forward_raw: bad argument");
+  if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
+  if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_forward_raw before yb_engine_load_weights");
+  if (e->C != 3) return fail(YB_ERR_INVALID, "raw BGR input needs a 3-channel network input, this one has %d", e->C);
+  // The reference passes (input_h, input_w) to cv2.resize as dsize = (width, height) (net/base.py:121): for a non-square
+  // network the resized array has shape (input_w, input_h, 3) and its [None, input_h, input_w, 3] placeholder rejects it.
+  if (e->H != e->W)
+    return fail(YB_ERR_INVALID, "non-square network input %dx%d: the reference's preprocess_image resizes to (%d, %d), which its placeholder rejects",
+                e->H, e->W, e->W, e->H);
+  YB_TRY(set_device(e->device));
+  const int slot = e->stage_toggle;
+  e->stage_toggle ^= 1;
+  YB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_input_free[slot], 0));
+  YB_TRY(e->pre.run(slot, e->copy_stream, e->stream, e->ev_copied[slot], images, heights, widths, strides, n, e->H, e->W,
+                    reinterpret_cast<unsigned char*>(e->input_dev[slot])));
+  e->cur_input = e->input_dev[slot];
+  e->cur_input_dtype = YB_U8;
+  e->last_input_is_u8_staged = true;
+  const int r = enqueue_ops(e, n, slot, nullptr, nullptr);
+  if (r == YB_OK) ++e->fwd_launches;      // the resize kernel
+  return r;
+}
+
+int yb_engine_read_input_u8(yb_engine* e, unsigned char* host_out, size_t capacity) {
+  if (!e || !host_out) return fail(YB_ERR_INVALID, "yb_engine_read_input_u8: bad argument");
+  if (e->last_n <= 0 || !e->last_input_is_u8_staged) return fail(YB_ERR_STATE, "yb_engine_read_input_u8 needs a preceding yb_engine_forward_raw");
+  const size_t total = (size_t)e->last_n * e->H * e->W * e->C;
+  if (capacity < total) return fail(YB_ERR_CAPACITY, "input needs %zu bytes, buffer holds %zu", total, capacity);
+  YB_TRY(set_device(e->device));
+  YB_CUDA(cudaMemcpyAsync(host_out, e->cur_input, total, cudaMemcpyDeviceToHost, e->stream));
+  YB_CUDA(cudaStreamSynchronize(e->stream));
+  return YB_OK;
+}
+
+// Stand-alone: cv2.resize(image, (dst_w, dst_h)) [INTER_LINEAR] + BGR->RGB for n host images into host memory
+// [n, dst_h, dst_w, 3] (kernel-level parity tests, any destination shape).
+int yb_resize_bgr2rgb(const void* const* images, const int* heights, const int* widths, const int* strides, int n, int dst_h, int dst_w,
+                      unsigned char* dst_host, int device) {
+  if (!images || !heights || !widths || !dst_host || n <= 0 || dst_h <= 0 || dst_w <= 0) return fail(YB_ERR_INVALID, "yb_resize_bgr2rgb: bad argument");
+  YB_TRY(set_device(device));
+  PreCtx pre;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev = nullptr;
+  unsigned char* d_out = nullptr;
+  const size_t total = (size_t)n * dst_h * dst_w * 3;
+  auto go = [&]() -> int {
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    YB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    YB_CUDA(cudaMalloc(&d_out, total));
+    YB_TRY(pre.run(0, st, st, ev, images, heights, widths, strides, n, dst_h, dst_w, d_out));
+    YB_CUDA(cudaMemcpyAsync(dst_host, d_out, total, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    return YB_OK;
+  };
+  const int r = go();
+  pre.release();
+  cudaFree(d_out);
+  if (ev) cudaEventDestroy(ev);
+  if (st) cudaStreamDestroy(st);
+  return r;
 }
 
 int yb_engine_output_shape(yb_engine* e, int* rows, int* cols) {

@@ -26,6 +26,29 @@ def _buffer(arr, np_dtypes):
     raise TypeError("expected a numpy array or a torch tensor")
 
 
+def _raw_image_args(images):
+    keep = []
+    n = len(images)
+    ptrs, hs, ws, strides = (ctypes.c_void_p * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    for i, im in enumerate(images):
+        im = np.asarray(im)
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise TypeError("image {}: expected a uint8 [h, w, 3] array, got {} {}".format(i, im.dtype, im.shape))
+        if im.strides[2] != 1 or im.strides[1] != 3 or im.strides[0] < im.shape[1] * 3:
+            im = np.ascontiguousarray(im)
+        keep.append(im)
+        ptrs[i], hs[i], ws[i], strides[i] = im.ctypes.data, im.shape[0], im.shape[1], im.strides[0]
+    return ptrs, hs, ws, strides, keep
+
+
+def resize_bgr2rgb(images, dst_h, dst_w, device=0):
+    """cv2.resize(image, (dst_w, dst_h)) [INTER_LINEAR] + BGR->RGB on the device: [n, dst_h, dst_w, 3] uint8."""
+    ptrs, hs, ws, strides, keep = _raw_image_args(images)
+    out = np.empty((len(images), dst_h, dst_w, 3), dtype=np.uint8)
+    _lib.check(_lib.lib().yb_resize_bgr2rgb(ptrs, hs, ws, strides, len(images), dst_h, dst_w, out.ctypes.data, device))
+    return out
+
+
 class Engine(object):
     """One compiled network on one GPU (yb_engine)."""
 
@@ -74,6 +97,20 @@ class Engine(object):
         self._keep = keep
         _lib.check(_lib.lib().yb_engine_forward(self._h, ptr, _lib.YB_F32 if dt == np.float32 else _lib.YB_U8, mem, shape[0]))
         self.last_n = shape[0]
+
+    def forward_raw(self, images):
+        """images: list of uint8 BGR arrays [h, w, 3] as cv2.imread returns them (any sizes).  Resize (cv2 INTER_LINEAR,
+        bit-exact), BGR->RGB and /255 run on the device, then the conv stack.  Asynchronous."""
+        ptrs, hs, ws, strides, keep = _raw_image_args(images)
+        self._keep = keep
+        _lib.check(_lib.lib().yb_engine_forward_raw(self._h, ptrs, hs, ws, strides, len(images)))
+        self.last_n = len(images)
+
+    def read_input_u8(self):
+        """The preprocessed uint8 RGB batch [n, H, W, 3] of the last forward_raw."""
+        out = np.empty((self.last_n,) + self.input_shape, dtype=np.uint8)
+        _lib.check(_lib.lib().yb_engine_read_input_u8(self._h, out.ctypes.data, out.size))
+        return out
 
     def read_output(self):
         """The reference's net[-1].out for the last forward, as float32 numpy."""

@@ -186,6 +186,59 @@ def load_checkpoint_by_path(saver, sess, checkpoint_path):
         return False
 
 
+def run_kmeans(data, num_anchors, tolerate, verbose=False):
+    """k-means over normalised (w, h) box sizes, the reference's call exactly (net/base.py:49-52): scikit-learn's
+    KMeans with its default initialisation, i.e. as non-deterministic as the reference unless numpy is seeded."""
+    import sklearn.cluster
+    km = sklearn.cluster.KMeans(n_clusters=num_anchors, tol=tolerate, verbose=verbose)
+    km.fit(data)
+    return km.cluster_centers_
+
+
+def parse_annotations(annotation_dir, image_dir, normalize=False):
+    """Pascal-VOC XML files -> [(image path, [(x1, y1, x2, y2, name), ...])] (net/base.py:69-97)."""
+    import xml.etree.ElementTree as ET
+    annotations = [os.path.join(os.path.abspath(annotation_dir), f) for f in os.listdir(annotation_dir)
+                   if f.lower().endswith(".xml")]
+    result = []
+    for annotation in annotations:
+        root = ET.parse(annotation).getroot()
+        img_path = os.path.join(image_dir, root.find("filename").text)
+        size = root.find("size")
+        w = int(size.find("width").text)
+        h = int(size.find("height").text)
+        img_objects = []
+        for obj in root.findall("object"):
+            name = obj.find("name").text
+            bndbox = obj.find("bndbox")
+            x1, y1 = int(bndbox.find("xmin").text), int(bndbox.find("ymin").text)
+            x2, y2 = int(bndbox.find("xmax").text), int(bndbox.find("ymax").text)
+            if normalize:
+                x1, x2 = x1 / w, x2 / w
+                y1, y2 = y1 / h, y2 / h
+            img_objects.append((x1, y1, x2, y2, name))
+        result.append((img_path, img_objects))
+    return result
+
+
+def boxes_to_arrays(boxes):
+    """list of BoundingBox (kept order) -> the (boxes, scores, classes) triple as arrays:
+    boxes float64 [k, 4] normalised centre-size (x, y, w, h), scores float32 [k], classes int64 [k]."""
+    k = len(boxes)
+    out_boxes = np.zeros((k, 4), dtype=np.float64)
+    scores = np.zeros(k, dtype=np.float32)
+    classes = np.zeros(k, dtype=np.int64)
+    for i, b in enumerate(boxes):
+        out_boxes[i] = (b.x, b.y, b.w, b.h)
+        scores[i], classes[i] = b.prob, b.class_idx
+    return out_boxes, scores, classes
+
+
+def boxes_to_corners(boxes, h=1., w=1.):
+    """[k, 4] (x1, y1, x2, y2) via BoundingBox.get_top_left / get_bottom_right (net/base.py:266-272)."""
+    return np.asarray([b.get_top_left(h, w) + b.get_bottom_right(h, w) for b in boxes], dtype=np.float64).reshape(-1, 4)
+
+
 def load_image_paths(path_to_img_dir):
     return [os.path.join(os.path.abspath(path_to_img_dir), f) for f in os.listdir(path_to_img_dir)
             if any(f.lower().endswith(ext) for ext in ["jpg", "bmp", "png", "gif"])]
@@ -213,6 +266,24 @@ def generate_test_batch(img_paths, batch_size, input_shape):
             images.append(np.expand_dims(image, axis=0))
             paths.append(img_paths[b * batch_size + i])
         yield np.concatenate(images, axis=0), paths
+
+
+def generate_raw_batch(img_paths, batch_size):
+    """Like generate_test_batch, but yields the decoded BGR uint8 images as cv2.imread returns them: resize, BGR->RGB
+    and /255 then run on the GPU (yb_engine_forward_raw), bit-identical to preprocess_image.  An unreadable file ends
+    the run like in the reference (preprocess_image prints and returns None, which its caller cannot unpack)."""
+    import cv2
+    total_batches = int(np.ceil(len(img_paths) / batch_size))
+    for b in range(total_batches):
+        images, paths = [], []
+        for path in img_paths[b * batch_size:(b + 1) * batch_size]:
+            image = cv2.imread(path)
+            if image is None:
+                print("Failed to read {}".format(path))
+                raise TypeError("cannot unpack non-iterable NoneType object")
+            images.append(image)
+            paths.append(path)
+        yield images, paths
 
 
 def non_maximum_suppression(boxes, iou_threshold):

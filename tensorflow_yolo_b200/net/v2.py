@@ -79,3 +79,28 @@ def find_bounding_boxes(net_out, net, threshold, iou_threshold, anchors, class_n
                                      _engine.YB_DECODE_V2, max_batch=net_out.shape[0], device=state.device)
         state.post = post
     return [base.boxes_from_dets(d) for d in post.run(net_out, threshold, iou_threshold)]
+
+
+@staticmethod
+def generate_anchors(params):
+    """ANCHOR mode (net/v2.py:298-323): k-means over the normalised (w, h) of every annotated box, scaled to grid
+    units of the network input (input_w / stride, input_h / stride).  Returns (flat anchors, set of class names)."""
+    num_anchors = int(params["num_anchors"])
+    image_dir = params["image_dir"]
+    annotation_dir = params["annotation_dir"]
+    tolerate = float(params["tolerate"])
+    stride = int(params["stride"])
+    input_w = int(params["input_w"])
+    input_h = int(params["input_h"])
+
+    annotations = base.parse_annotations(annotation_dir, image_dir, normalize=True)
+    print("{} annotations found.".format(len(annotations)))
+    class_names = set()
+    data = []
+    for annotation in annotations:
+        for o in annotation[1]:
+            data.append([float(o[2] - o[0]), float(o[3] - o[1])])
+            class_names.add(o[-1])
+    anchors = base.run_kmeans(data, num_anchors, tolerate)
+    anchors = [[a[0] * input_w / stride, a[1] * input_h / stride] for a in anchors]
+    return np.reshape(anchors, [-1]), class_names

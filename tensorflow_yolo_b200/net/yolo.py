@@ -1,4 +1,5 @@
 """TEST driver with the reference's class layout (net/yolo.py:12-96, 198-211)."""
+import concurrent.futures
 import os
 
 import numpy as np
@@ -20,6 +21,13 @@ class Yolo(object):
         state = base.state_of(net)
         eng = state.ensure_engine(len(x_batch))
         eng.forward(np.asarray(x_batch))
+        return [base.boxes_from_dets(d) for d in eng.detect(threshold, iou_threshold)]
+
+    def detect_batch_raw(self, net, raw_images, threshold, iou_threshold):
+        """detect_batch on decoded BGR images: preprocessing (net/base.py:115-155) runs on the GPU as well."""
+        state = base.state_of(net)
+        eng = state.ensure_engine(len(raw_images))
+        eng.forward_raw(raw_images)
         return [base.boxes_from_dets(d) for d in eng.detect(threshold, iou_threshold)]
 
     def test(self, params):
@@ -52,30 +60,56 @@ class Yolo(object):
             else:
                 print("Checkpoint {} restored.".format(checkpoint_path))
 
-            for x_batch, paths in base.generate_test_batch(image_paths, batch_size, input_shape):
-                net_boxes = self.detect_batch(net, x_batch, threshold, iou_threshold)
-                for boxes, path in zip(net_boxes, paths):
-                    results[path] = boxes
-                    new_img = base.draw_boxes(path, boxes, class_names)
-                    file_name, file_ext = os.path.splitext(os.path.basename(path))
-                    out_path = os.path.join(out_dir, "{}_out{}".format(file_name, file_ext))
-                    os.makedirs(out_dir, exist_ok=True)
-                    base.save_image(new_img, out_path)
-                    print("{}: Found {} objects. Saved to {}".format(file_name, len(boxes), out_path))
+            # Device preprocessing needs what the reference needs anyway (square 3-channel input, see
+            # yb_engine_forward_raw); YB_HOST_PREPROCESS=1 keeps the reference's host-side cv2 protocol.
+            on_device = (input_shape[0] == input_shape[1] and input_shape[2] == 3 and
+                         os.environ.get("YB_HOST_PREPROCESS", "0") != "1")
+            if on_device:
+                batches = ((self.detect_batch_raw(net, raw, threshold, iou_threshold), paths)
+                           for raw, paths in base.generate_raw_batch(image_paths, batch_size))
+            else:
+                batches = ((self.detect_batch(net, x_batch, threshold, iou_threshold), paths)
+                           for x_batch, paths in base.generate_test_batch(image_paths, batch_size, input_shape))
+            # Drawing and saving (net/base.py:212-230, cv2 on the host) run on a worker thread so the GPU is already on
+            # the next batch; the per-image lines are printed in the reference's order.
+            os.makedirs(out_dir, exist_ok=True)
+
+            def draw_and_save(path, boxes):
+                new_img = base.draw_boxes(path, boxes, class_names)
+                file_name, file_ext = os.path.splitext(os.path.basename(path))
+                out_path = os.path.join(out_dir, "{}_out{}".format(file_name, file_ext))
+                base.save_image(new_img, out_path)
+                return "{}: Found {} objects. Saved to {}".format(file_name, len(boxes), out_path)
+
+            pending = []
+            with concurrent.futures.ThreadPoolExecutor(max_workers=int(os.environ.get("YB_DRAW_THREADS", "4"))) as pool:
+                for net_boxes, paths in batches:
+                    for boxes, path in zip(net_boxes, paths):
+                        results[path] = boxes
+                        pending.append(pool.submit(draw_and_save, path, boxes))
+                    while pending and pending[0].done():
+                        print(pending.pop(0).result())
+                for fut in pending:
+                    print(fut.result())
             print("Done")
         return results
+
+    def predict(self, params):
+        """test() plus the structured result: {image path: (boxes [k,4] centre-size, scores [k], classes [k])}."""
+        return {path: base.boxes_to_arrays(boxes) for path, boxes in (self.test(params) or {}).items()}
 
     def train(self, params):
         raise NotImplementedError("training is outside the scope of tensorflow_yolo_b200 (TEST path only)")
 
     def generate_anchors(self, params):
-        raise NotImplementedError("ANCHOR mode is outside the scope of tensorflow_yolo_b200 (TEST path only)")
+        raise NotImplementedError()        # like the reference: bound for YoloV2 only (net/yolo.py:198-205)
 
 
 class YoloV2(Yolo):
     create_network = v2.create_full_network
     load_weights = v2.load_weights
     find_bounding_boxes = v2.find_bounding_boxes
+    generate_anchors = v2.generate_anchors
 
 
 class YoloV3(Yolo):
