@@ -162,6 +162,8 @@ struct PostCtx {
   int* cls = nullptr;
   unsigned long long* keys = nullptr;
   void* sorted_boxes = nullptr;
+  float4 *sorted_f4 = nullptr, *sorted_f4i = nullptr;
+  float2* sorted_area = nullptr;
   int* sorted_cls = nullptr;
   unsigned char* flags = nullptr;
   int *order = nullptr, *n_keep = nullptr, *n_cand = nullptr;
@@ -179,6 +181,9 @@ struct PostCtx {
     YB_CUDA(cudaMalloc(&w, nr * 8)); YB_CUDA(cudaMalloc(&h, nr * 8)); YB_CUDA(cudaMalloc(&cls, nr * 4));
     if (rows_pow2 > NMS_SMEM_KEYS) YB_CUDA(cudaMalloc(&keys, (size_t)max_batch * rows_pow2 * 8));
     YB_CUDA(cudaMalloc(&sorted_boxes, nr * sizeof(BoxC<double>)));
+    YB_CUDA(cudaMalloc(&sorted_f4, nr * sizeof(float4)));
+    YB_CUDA(cudaMalloc(&sorted_f4i, nr * sizeof(float4)));
+    YB_CUDA(cudaMalloc(&sorted_area, nr * sizeof(float2)));
     YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
     YB_CUDA(cudaMalloc(&order, nr * 4));
     YB_CUDA(cudaMalloc(&n_keep, (size_t)max_batch * 4)); YB_CUDA(cudaMalloc(&n_cand, (size_t)max_batch * 4));
@@ -188,7 +193,7 @@ struct PostCtx {
   }
   void release() {
     cudaFree(prob); cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(h); cudaFree(cls); cudaFree(keys);
-    cudaFree(sorted_boxes); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
+    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
     cudaFree(dets);
     for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
   }
@@ -200,9 +205,12 @@ struct PostCtx {
     for (int i = 0; i < n_scales; ++i) a.sc[i] = sc[i];
     a.n_scales = n_scales; a.rows = rows; a.box_len = box_len; a.n_images = n; a.v2 = v2; a.thr = thr;
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    const long long warps = (long long)n * rows;
-    const int blocks = ceil_div(warps * 32, 256);
-    decode_kernel<<<blocks, 256, 0, st>>>(a);
+    if (!v2) {       // one lane per row (+ cooperative decode of the candidates)
+      decode_v3_kernel<<<ceil_div((long long)n * rows, 256), 256, 0, st>>>(a);
+    } else {         // one warp per row: the softmax score needs the whole row anyway
+      const long long warps = (long long)n * rows;
+      decode_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(a);
+    }
     YB_CUDA(cudaGetLastError());
     return YB_OK;
   }
@@ -222,7 +230,7 @@ struct PostCtx {
     memset(&a, 0, sizeof(a));
     a.rows = rows; a.per_class = per_class; a.thr = thr;
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_cls = sorted_cls;
+    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
     a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;
     return a;
   }

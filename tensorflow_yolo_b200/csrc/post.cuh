@@ -146,6 +146,106 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
   }
 }
 
+// YOLOv3 decode, restructured around the fact that the keep/drop decision needs ONE logit per row (net/v3.py:123-125):
+//   phase 1  one lane per row: load t_obj, score = sigmoid(t_obj), write the dense score (NaN = not a candidate);
+//   phase 2  the warp walks its candidate rows (ballot) and decodes each cooperatively: coalesced read of the row,
+//            class argmax, box maths spread over four lanes.
+// Sparse heads (real images: a few candidates per image) therefore touch one 32-byte sector per row instead of the
+// whole row.  The class argmax works on d = 1 + exp(-t) instead of sigmoid(t) = 1 / d: the correctly rounded division is
+// monotone, so argmax sigmoid == argmin d, and np.argmax's "first of the maxima" only needs the quotient for the rare
+// near-ties of d (one division per row instead of one per class).
+__global__ void __launch_bounds__(256) decode_v3_kernel(const DecodeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)a.n_images * a.rows;
+  const long long warp_first = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;   // first row of this warp
+  if (warp_first >= total) return;
+  const long long gr = warp_first + lane;
+  const int len = a.box_len;
+  // ---- phase 1 ----
+  const float* p = nullptr;
+  int cell = 0, anc = 0, s = 0;
+  bool cand = false;
+  if (gr < total) {
+    const int img = (int)(gr / a.rows);
+    const int row = (int)(gr - (long long)img * a.rows);
+#pragma unroll
+    for (int i = 1; i < POST_MAX_SCALES; ++i)
+      if (i < a.n_scales && row >= a.sc[i].row_begin) s = i;
+    const ScaleDesc& sc = a.sc[s];
+    const int local = row - sc.row_begin;
+    cell = local / sc.na;
+    anc = local - cell * sc.na;
+    p = sc.base + (long long)img * sc.img_stride + (long long)cell * sc.cell_stride + anc * len;
+    const float obj = sigmoid_ref(__ldg(p + 4));
+    cand = obj >= a.thr;
+    a.prob[gr] = cand ? obj : __int_as_float(0x7fc00000);
+  }
+  // ---- phase 2a: box maths, one lane per candidate row (the five box logits share the sector t_obj came from) ----
+  if (cand) {
+    const ScaleDesc& sc = a.sc[s];
+    const float t0 = __ldg(p), t1 = __ldg(p + 1), t2 = __ldg(p + 2), t3 = __ldg(p + 3);
+    const int cy = cell / sc.w;
+    const int cx = cell - cy * sc.w;
+    a.x[gr] = __fdiv_rn(__fadd_rn(sigmoid_ref(t0), (float)cx), (float)sc.w);      // (sigmoid(tx) + cx) / w
+    a.y[gr] = __fdiv_rn(__fadd_rn(sigmoid_ref(t1), (float)cy), (float)sc.h);
+    // anchors are float64 in the reference: (aw * exp(tw)) / w evaluated in float64
+    a.w[gr] = __ddiv_rn(__dmul_rn((double)sc.anchors[2 * anc], (double)expf(t2)), (double)sc.w);
+    a.h[gr] = __ddiv_rn(__dmul_rn((double)sc.anchors[2 * anc + 1], (double)expf(t3)), (double)sc.h);
+  }
+  // ---- phase 2b: class argmax, four candidate rows at a time, eight lanes per row ----
+  unsigned mask = __ballot_sync(0xffffffffu, cand);
+  const int sub = lane >> 3, sl = lane & 7;
+  const unsigned gmask = 0xFFu << (sub * 8);
+  while (mask) {
+    int my_src = -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int src = mask ? __ffs(mask) - 1 : -1;
+      if (mask) mask &= mask - 1;
+      if (q == sub) my_src = src;
+    }
+    const float* rp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)p, my_src < 0 ? 0 : my_src));
+    // per lane: smallest d = 1 + exp(-t) of its classes (lowest index on ties) and the runner-up
+    float dmin = INFINITY, d2 = INFINITY;
+    int kmin = 0x7fffffff;
+    if (my_src >= 0) {
+#pragma unroll 5
+      for (int k = 5 + sl; k < len; k += 8) {
+        const float d = __fadd_rn(1.0f, expf(-__ldg(rp + k)));
+        if (d < dmin) { d2 = dmin; dmin = d; kmin = k - 5; }
+        else if (d < d2) d2 = d;
+      }
+    }
+    float wd = dmin;
+    int wk = kmin;
+#pragma unroll
+    for (int sft = 4; sft > 0; sft >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, wd, sft);
+      const int ok = __shfl_xor_sync(0xffffffffu, wk, sft);
+      if (od < wd || (od == wd && ok < wk)) { wd = od; wk = ok; }
+    }
+    // Near-ties: another class whose d is within a few ulps of the minimum may round to the same sigmoid and, having a
+    // lower index, be np.argmax's answer; so may any class once 1/d is subnormal.  Rare: only then are the exact
+    // quotients computed (by the eight lanes of that row).
+    const float near = wd * 1.000001f;
+    const bool tie = my_src >= 0 && ((kmin != wk && dmin <= near) || (d2 <= near) || !(wd < 1e37f));
+    const unsigned ties = __ballot_sync(0xffffffffu, tie);
+    int best_k = wk;
+    if (ties & gmask) {
+      const float smax = __fdiv_rn(1.0f, wd);
+      int cand_k = 0x7fffffff;
+      for (int k = 5 + sl; k < len; k += 8) {
+        const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__ldg(rp + k))));
+        if (sg == smax && k - 5 < cand_k) cand_k = k - 5;
+      }
+#pragma unroll
+      for (int sft = 4; sft > 0; sft >>= 1) cand_k = min(cand_k, __shfl_xor_sync(gmask, cand_k, sft));
+      best_k = cand_k;
+    }
+    if (my_src >= 0 && sl == 0) a.cls[warp_first + my_src] = best_k;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // sort + NMS
 // ----------------------------------------------------------------------------------------------
@@ -206,6 +306,73 @@ __device__ __forceinline__ bool box_finite(const BoxC<T>& b) {
   return isfinite(b.x1) && isfinite(b.y1) && isfinite(b.x2) && isfinite(b.y2) && isfinite(b.area);
 }
 
+// The reference's decision "iou_score(p, q) >= thr" (strict: ">", the per-class mode) for two FINITE boxes without
+// paying for the division in the common case: with u the unit round-off, fl(inter/uni) and fl(thr*uni) are each
+// within a factor (1 +- u) of the exact values, so whenever inter differs from fl(thr*uni) by more than a relative
+// margin m >> u the comparison of the rounded quotient with thr is decided; only the rare near-ties take the exact
+// division, which keeps every decision bit-identical to iou_ref.
+template <typename T>
+__device__ __forceinline__ bool suppresses_finite(const BoxC<T>& p, const BoxC<T>& q, T thr, bool strict) {
+  using A = Arith<T>;
+  const T ix1 = p.x1 > q.x1 ? p.x1 : q.x1, iy1 = p.y1 > q.y1 ? p.y1 : q.y1;
+  const T ix2 = p.x2 < q.x2 ? p.x2 : q.x2, iy2 = p.y2 < q.y2 ? p.y2 : q.y2;
+  T iw = A::sub(ix2, ix1), ih = A::sub(iy2, iy1);
+  iw = iw > (T)0 ? iw : (T)0;
+  ih = ih > (T)0 ? ih : (T)0;
+  const T inter = A::mul(iw, ih);
+  T uni = A::sub(A::add(p.area, q.area), inter);
+  uni = uni > (T)1e-8 ? uni : (T)1e-8;
+  if (thr > (T)0) {
+    const T m = sizeof(T) == 8 ? (T)1e-12 : (T)1e-5;
+    const T tq = A::mul(thr, uni);
+    const T d = A::sub(inter, tq), band = A::mul(m, tq);
+    if (d > band) return true;
+    if (d < -band) return false;
+  }
+  const T v = A::div(inter, uni);
+  return strict ? (v > thr) : (v >= thr);
+}
+
+// float32 interval arithmetic on the float64 box (T = double only).  A box carries outward- and inward-rounded float
+// copies of its corners and down-/up-rounded copies of its area, so [lo, hi] float bounds of the REAL-arithmetic
+// intersection and union follow with directed-rounding float ops; the float64 result iou_ref computes differs from
+// the real-arithmetic IoU by a relative ~1e-15, so a bound that clears thr by a relative 1e-6 decides the comparison
+// for certain.  Returns +1 (suppresses), -1 (does not), 0 (too close: take the exact float64 path).
+struct BoxF {
+  float4 out;     // rd(x1), rd(y1), ru(x2), ru(y2)
+  float4 in;      // ru(x1), ru(y1), rd(x2), rd(y2)
+  float2 area;    // rd(area), ru(area)
+};
+__device__ __forceinline__ BoxF make_boxf(double x1, double y1, double x2, double y2, double area) {
+  BoxF f;
+  f.out = make_float4(__double2float_rd(x1), __double2float_rd(y1), __double2float_ru(x2), __double2float_ru(y2));
+  f.in = make_float4(__double2float_ru(x1), __double2float_ru(y1), __double2float_rd(x2), __double2float_rd(y2));
+  f.area = make_float2(__double2float_rd(area), __double2float_ru(area));
+  return f;
+}
+__device__ __forceinline__ int decide_f32(const float4& po, const float4& pi, const float2& pa, const float4& qo, const float4& qi,
+                                          const float2& qa, float thr_dn, float thr_up) {
+  const float iw_hi = fmaxf(__fsub_ru(fminf(po.z, qo.z), fmaxf(po.x, qo.x)), 0.0f);
+  const float ih_hi = fmaxf(__fsub_ru(fminf(po.w, qo.w), fmaxf(po.y, qo.y)), 0.0f);
+  const float iw_lo = fmaxf(__fsub_rd(fminf(pi.z, qi.z), fmaxf(pi.x, qi.x)), 0.0f);
+  const float ih_lo = fmaxf(__fsub_rd(fminf(pi.w, qi.w), fmaxf(pi.y, qi.y)), 0.0f);
+  const float inter_hi = __fmul_ru(iw_hi, ih_hi), inter_lo = __fmul_rd(iw_lo, ih_lo);
+  const float uni_hi = fmaxf(__fsub_ru(__fadd_ru(pa.y, qa.y), inter_lo), 1.0000001e-8f);
+  const float uni_lo = fmaxf(__fsub_rd(__fadd_rd(pa.x, qa.x), inter_hi), 9.9999999e-9f);
+  if (inter_lo > __fmul_ru(thr_up, uni_hi)) return 1;      // IoU >= inter_lo / uni_hi > thr (1 + 1e-6)
+  if (inter_hi < __fmul_rd(thr_dn, uni_lo)) return -1;     // IoU <= inter_hi / uni_lo < thr (1 - 1e-6)
+  return 0;
+}
+
+// Outward-rounded float copies of a box's corners: if two such intervals do not overlap, neither do the exact ones.
+__device__ __forceinline__ float4 conservative_f4(double x1, double y1, double x2, double y2) {
+  return make_float4(__double2float_rd(x1), __double2float_rd(y1), __double2float_ru(x2), __double2float_ru(y2));
+}
+// true: the boxes certainly share no area (intersection width or height <= 0), i.e. inter == 0 and iou == 0
+__device__ __forceinline__ bool surely_disjoint(const float4& a, const float4& b) {
+  return a.z <= b.x || b.z <= a.x || a.w <= b.y || b.w <= a.y;
+}
+
 struct NmsArgs {
   int rows;             // R: dense rows per image (stride of every per-row array)
   int per_class;        // 0: reference (class-agnostic, >=); 1: per class, strict >
@@ -221,6 +388,9 @@ struct NmsArgs {
   unsigned long long* keys;   // global sort scratch, rows_pow2 per image (used when K_pow2 > smem keys)
   int rows_pow2;
   void* sorted_boxes;   // BoxC<T> [n * rows]
+  float4* sorted_f4;    // [n * rows]: outward-rounded float corners of the sorted boxes (disjointness prefilter)
+  float4* sorted_f4i;   // [n * rows]: inward-rounded float corners          } float interval arithmetic,
+  float2* sorted_area;  // [n * rows]: area rounded down / up to float       } see decide_f32
   int* sorted_cls;      // [n * rows]
   unsigned char* flags; // [n * rows] bit0: removed, bit1: kept, bit2: non-finite box
   // outputs
@@ -261,7 +431,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   __shared__ int s_count;
   __shared__ unsigned long long s_mask[NMS_BLOCK];
   __shared__ unsigned long long s_kept_mask;
+  __shared__ unsigned s_alive[2];
+  __shared__ BoxC<T> s_kbox[NMS_BLOCK];        // the kept boxes of the current block, compacted
+  __shared__ float4 s_kf4[NMS_BLOCK];
+  __shared__ float4 s_kf4i[NMS_BLOCK];
+  __shared__ float2 s_karea[NMS_BLOCK];
+  __shared__ int s_kcls[NMS_BLOCK];
+  __shared__ unsigned char s_knf[NMS_BLOCK];
   __shared__ BoxC<T> s_box[NMS_BLOCK];
+  __shared__ float4 s_f4[NMS_BLOCK];
   __shared__ int s_cls[NMS_BLOCK];
   __shared__ unsigned char s_nf[NMS_BLOCK];
   __shared__ int s_scan[32];
@@ -312,6 +490,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
 
   // ---- 3. gather sorted boxes ----
   BoxC<T>* sb = reinterpret_cast<BoxC<T>*>(a.sorted_boxes) + base;
+  float4* sf4 = a.sorted_f4 + base;
+  float4* sf4i = a.sorted_f4i + base;
+  float2* sarea = a.sorted_area + base;
   int* scls = a.sorted_cls + base;
   unsigned char* flags = a.flags + base;
   int* order = a.order + base;
@@ -324,6 +505,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     const T bh = WH64 ? (T) reinterpret_cast<const double*>(a.h)[base + r] : (T) reinterpret_cast<const float*>(a.h)[base + r];
     const BoxC<T> b = make_box<T>(bx, by, bw, bh);
     sb[i] = b;
+    const BoxF bf = make_boxf((double)b.x1, (double)b.y1, (double)b.x2, (double)b.y2, (double)b.area);
+    sf4[i] = bf.out; sf4i[i] = bf.in; sarea[i] = bf.area;
     scls[i] = a.cls ? a.cls[base + r] : 0;
     flags[i] = box_finite(b) ? 0 : 4;
     order[i] = r;          // provisional: sorted row ids; compacted to kept rows in step 5
@@ -333,35 +516,44 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   // ---- 4. blocked greedy sweep ----
   const T thr = (T)a.thr;
   const bool per_class = a.per_class != 0;
+  // iou == 0 never suppresses when thr > 0 (>=) / thr >= 0 (>): then surely disjoint pairs are skipped outright
+  const bool skip_disjoint = per_class ? (thr >= (T)0) : (thr > (T)0);
+  // float interval fast path (float64 boxes, positive threshold): bounds of thr (1 -+ 1e-6) rounded outwards
+  const bool use_f32 = sizeof(T) == 8 && a.thr > 1e-30 && a.thr < 1e30;
+  const float thr_dn = __double2float_rd(a.thr * 0.999999), thr_up = __double2float_ru(a.thr * 1.000001);
   for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
     const int nb = min(NMS_BLOCK, K - b0);
     if (tid < NMS_BLOCK) {
       s_mask[tid] = 0ull;
-      if (tid < nb) { s_box[tid] = sb[b0 + tid]; s_cls[tid] = scls[b0 + tid]; s_nf[tid] = flags[b0 + tid] & 4; }
+      if (tid < nb) { s_box[tid] = sb[b0 + tid]; s_f4[tid] = sf4[b0 + tid]; s_cls[tid] = scls[b0 + tid]; s_nf[tid] = flags[b0 + tid] & 4; }
     }
     __syncthreads();
     // 4a. intra-block pair mask: bit j of s_mask[i] set iff i<j and box i suppresses box j
     for (int pidx = tid; pidx < NMS_BLOCK * NMS_BLOCK; pidx += NMS_THREADS) {
       const int i = pidx >> 6, j = pidx & 63;
       if (i < j && j < nb) {
+        if (per_class && s_cls[i] != s_cls[j]) continue;
         bool sup;
-        if (s_nf[i] | s_nf[j] | (sizeof(T) == 4)) {
+        if (s_nf[i] | s_nf[j]) {
           const T v = iou_ref<T, true>(s_box[i], s_box[j]);
           sup = per_class ? (v > thr) : (v >= thr);
         } else {
-          const T v = iou_ref<T, false>(s_box[i], s_box[j]);
-          sup = per_class ? (v > thr) : (v >= thr);
+          if (skip_disjoint && surely_disjoint(s_f4[i], s_f4[j])) continue;
+          sup = suppresses_finite<T>(s_box[i], s_box[j], thr, per_class);
         }
-        if (per_class && s_cls[i] != s_cls[j]) sup = false;
         if (sup) atomicOr(&s_mask[i], 1ull << j);
       }
     }
     __syncthreads();
-    // 4b. sequential resolution of the block by one thread
+    // 4b. sequential resolution of the block by one thread (everything it touches is in shared memory / registers)
+    if (tid < 64) {
+      const bool alive_t = tid < nb && !(flags[b0 + tid] & 1);
+      const unsigned bal = __ballot_sync(0xffffffffu, alive_t);
+      if ((tid & 31) == 0) s_alive[tid >> 5] = bal;
+    }
+    __syncthreads();
     if (tid == 0) {
-      unsigned long long alive = 0ull;
-      for (int i = 0; i < nb; ++i)
-        if (!(flags[b0 + i] & 1)) alive |= (1ull << i);
+      unsigned long long alive = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
       unsigned long long kept = 0ull;
       for (int i = 0; i < nb; ++i) {
         if (alive & (1ull << i)) {
@@ -373,26 +565,71 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     }
     __syncthreads();
     const unsigned long long kept = s_kept_mask;
-    if (tid < nb && (kept >> tid) & 1ull) flags[b0 + tid] |= 2;
-    // 4c. every kept box of this block suppresses all later boxes
-    if (kept != 0ull) {
+    const int nkept = __popcll(kept);
+    if (tid < nb && (kept >> tid) & 1ull) {
+      flags[b0 + tid] |= 2;
+      // compact copy of the kept boxes of this block; a non-finite box gets an all-covering float box so the
+      // disjointness test never drops it
+      const int pos = __popcll(kept & ((1ull << tid) - 1ull));
+      s_kbox[pos] = s_box[tid];
+      s_kcls[pos] = s_cls[tid];
+      s_knf[pos] = s_nf[tid];
+      s_kf4[pos] = s_nf[tid] ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY) : s_f4[tid];
+      s_kf4i[pos] = sf4i[b0 + tid];
+      s_karea[pos] = sarea[b0 + tid];
+    }
+    __syncthreads();
+    // 4c. every kept box of this block suppresses all later boxes.  Two passes per later box j so that the lanes of a
+    // warp stay together: first the cheap float test against all kept boxes (bit q of a mask = kept box q may overlap
+    // j), then the exact decision only for the boxes in the mask -- a few per j even in the dense case.
+    if (nkept > 0) {
       for (int j = b0 + NMS_BLOCK + tid; j < K; j += NMS_THREADS) {
         const unsigned char fj = flags[j];
         if (fj & 1) continue;
-        const BoxC<T> bj = sb[j];
         const int cj = per_class ? scls[j] : 0;
-        unsigned long long m = kept;
+        unsigned lo = 0xffffffffu, hi = 0xffffffffu;
+        if (skip_disjoint && !(fj & 4)) {
+          const float4 f4j = sf4[j];
+          lo = hi = 0u;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float4 fa = s_kf4[q], fb = s_kf4[q + 32];      // entries >= nkept are stale but masked off below
+            lo |= surely_disjoint(fa, f4j) ? 0u : (1u << q);
+            hi |= surely_disjoint(fb, f4j) ? 0u : (1u << q);
+          }
+        }
+        unsigned long long todo = ((unsigned long long)hi << 32) | lo;
+        if (nkept < 64) todo &= (1ull << nkept) - 1ull;
+        if (todo == 0ull) continue;
         bool sup = false;
-        while (m && !sup) {
-          const int i = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          if (per_class && s_cls[i] != cj) continue;
-          if ((fj & 4) | s_nf[i] | (sizeof(T) == 4)) {
-            const T v = iou_ref<T, true>(s_box[i], bj);
-            sup = per_class ? (v > thr) : (v >= thr);
-          } else {
-            const T v = iou_ref<T, false>(s_box[i], bj);
-            sup = per_class ? (v > thr) : (v >= thr);
+        if (use_f32 && !(fj & 4)) {
+          // float interval pass over the boxes that may overlap: decides all but near-threshold pairs
+          const float4 oj = sf4[j], ij = sf4i[j];
+          const float2 aj = sarea[j];
+          unsigned long long unsure = 0ull;
+          while (todo && !sup) {
+            const int q = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            if (per_class && s_kcls[q] != cj) continue;
+            if (s_knf[q]) { unsure |= 1ull << q; continue; }
+            const int d = decide_f32(s_kf4[q], s_kf4i[q], s_karea[q], oj, ij, aj, thr_dn, thr_up);
+            sup = d > 0;
+            if (d == 0) unsure |= 1ull << q;
+          }
+          todo = sup ? 0ull : unsure;
+        }
+        if (todo) {
+          const BoxC<T> bj = sb[j];
+          while (todo && !sup) {
+            const int q = __ffsll((long long)todo) - 1;
+            todo &= todo - 1;
+            if (per_class && s_kcls[q] != cj) continue;
+            if ((fj & 4) | s_knf[q]) {
+              const T v = iou_ref<T, true>(s_kbox[q], bj);
+              sup = per_class ? (v > thr) : (v >= thr);
+            } else {
+              sup = suppresses_finite<T>(s_kbox[q], bj, thr, per_class);
+            }
           }
         }
         if (sup) flags[j] = fj | 1;

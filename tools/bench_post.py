@@ -50,8 +50,15 @@ def main():
             if best is None or d + n < best[0] + best[1]:
                 best = (d, n)
         kept = post.run(head[:4], thr, 0.6)
-        row = {"decode_ms": best[0], "nms_ms": best[1], "decode_GBps": B * R * L * 4 / (best[0] * 1e-3) / 1e9,
-               "decode_frac_of_hbm_peak": B * R * L * 4 / (best[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        cand = int(post.last_candidates.sum()) if False else None
+        head_bytes = B * R * L * 4
+        # dense: every row is a candidate, the whole head is read once (algorithmic bytes = head bytes).  sparse: a
+        # non-candidate row costs one 32-byte sector (its objectness logit) + a 4-byte score write.
+        touched = head_bytes if shift is None else B * R * 36
+        row = {"decode_ms": best[0], "nms_ms": best[1], "decode_algorithmic_bytes": touched,
+               "decode_GBps": touched / (best[0] * 1e-3) / 1e9,
+               "decode_frac_of_hbm_peak": touched / (best[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+               "decode_head_GBps_effective": head_bytes / (best[0] * 1e-3) / 1e9,
                "images_per_s": B / ((best[0] + best[1]) * 1e-3), "candidates_img0": int(post.last_candidates[0]),
                "kept_first4": [len(k) for k in kept]}
         out[name] = row
