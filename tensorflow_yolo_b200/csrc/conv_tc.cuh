@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace yb {
 
 enum OutMode { OUT_PLAIN = 0, OUT_UPSAMPLE2 = 1, OUT_REORG2 = 2 };
@@ -282,6 +284,7 @@ struct PersistArgs {
                        // ksub * BK/16 MMAs, so narrow tiles still give the tensor pipe >= ~500 cycles per hand-shake
   int b_stationary;    // 1: the whole [BN x K] weight matrix is loaded once per CTA and stays in shared memory
   int tma_epi;         // 1: bf16 plain output through smem + TMA store, residual through TMA load
+  int solo_issue;      // 1: a single thread runs the MMA issue loop; 0: the whole warp walks it, electing per stage
   int ablate;          // debug/roofline probes (results are wrong when non-zero): 1 = epilogue does nothing,
                        // 2 = no MMAs, 4 = no A loads, 8 = no B loads
   unsigned long long* dbg;   // optional [16] cycle counters summed over all CTAs (see CONV_DBG_*); nullptr = off
@@ -397,54 +400,64 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       uint32_t phase = 0;
       const int hw = a.Ho * a.Wo;
       const uint32_t full0 = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;       // leader's full_bar[0]
+      // KS: BK-blocks per stage as a compile-time constant (0 = runtime value, any remainder).  The producer's loop
+      // latency bounds the TMA issue rate, so the common cases are kept free of the runtime inner loop.
+      auto produce = [&](auto ks_tag) {
+        constexpr int KS = decltype(ks_tag)::value;
       for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step) {
-        const int tile_mj = tile / pa.n_tiles_n;
-        const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
-        const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;
-        const int m0 = tile_m * 128;
-        int img = 0, base_w = 0, base_h = 0;
-        if (a.im2col) {
-          img = m0 / hw;
-          const int rem = m0 - img * hw;
-          const int p0 = rem / a.Wo;
-          base_w = (rem - p0 * a.Wo) * a.conv_stride - a.pad;
-          base_h = p0 * a.conv_stride - a.pad;
-        }
-        int cb = 0, kh = 0, kw = 0;
-        for (int kb0 = 0; kb0 < num_k; kb0 += ksub) {
-          const int cnt = (num_k - kb0 < ksub) ? num_k - kb0 : ksub;      // BK-blocks in this stage
-          const long long t0 = dbg ? clk() : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (dbg) t_wait += clk() - t0;
-          uint8_t* st_base = stages + stage * stage_bytes;
-          const uint32_t fb = PAIR ? full0 + (uint32_t)stage * 8u : 0u;
-          if (PAIR) {
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes * (uint32_t)cnt);   // bytes of both CTAs
-            else mbar_arrive_cluster(fb);
-          } else {
-            mbar_expect_tx(&full_bar[stage], tx_bytes * (uint32_t)cnt);
+          const int tile_mj = tile / pa.n_tiles_n;
+          const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
+          const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;
+          const int m0 = tile_m * 128;
+          int img = 0, base_w = 0, base_h = 0;
+          if (a.im2col) {
+            img = m0 / hw;
+            const int rem = m0 - img * hw;
+            const int p0 = rem / a.Wo;
+            base_w = (rem - p0 * a.Wo) * a.conv_stride - a.pad;
+            base_h = p0 * a.conv_stride - a.pad;
           }
-          for (int j = 0; j < cnt; ++j) {
-            uint8_t* sa = st_base + j * sub_bytes;
-            const int kb = kb0 + j;
+          int cb = 0, kh = 0, kw = 0;
+          for (int kb0 = 0; kb0 < num_k; kb0 += (KS ? KS : ksub)) {
+            const int cnt = KS ? KS : ((num_k - kb0 < ksub) ? num_k - kb0 : ksub);      // BK-blocks in this stage
+            const long long t0 = dbg ? clk() : 0;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (dbg) t_wait += clk() - t0;
+            uint8_t* st_base = stages + stage * stage_bytes;
+            const uint32_t fb = PAIR ? full0 + (uint32_t)stage * 8u : 0u;
             if (PAIR) {
-              if (load_a) {
-                if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-                else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
-              }
-              if (load_b) tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes * (uint32_t)cnt);   // bytes of both CTAs
+              else mbar_arrive_cluster(fb);
             } else {
-              if (load_a) {
-                if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
-                else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
-              }
-              if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+              mbar_expect_tx(&full_bar[stage], tx_bytes * (uint32_t)cnt);
             }
-            if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+            for (int j = 0; j < cnt; ++j) {
+              uint8_t* sa = st_base + j * sub_bytes;
+              const int kb = kb0 + j;
+              if (PAIR) {
+                if (load_a) {
+                  if (a.im2col) tma_load_im2col_4d_pair(&tmA, fb, sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+                  else tma_load_2d_pair(&tmA, fb, sa, cb * BK, m0);
+                }
+                if (load_b) tma_load_2d_pair(&tmB, fb, sa + A_BYTES, kb * BK, n0 + (int)rank * (BN / 2));
+              } else {
+                if (load_a) {
+                  if (a.im2col) tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, base_w, base_h, img, (uint16_t)kw, (uint16_t)kh);
+                  else tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+                }
+                if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
+              }
+              if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+            }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-      }
+      };
+      if (ksub == 1) produce(std::integral_constant<int, 1>{});
+      else if (ksub == 2 && num_k % 2 == 0) produce(std::integral_constant<int, 2>{});
+      else if (ksub == 3 && num_k % 3 == 0) produce(std::integral_constant<int, 3>{});
+      else if (ksub == 9 && num_k % 9 == 0) produce(std::integral_constant<int, 9>{});
+      else produce(std::integral_constant<int, 0>{});
       if (dbg) {
         atomicAdd(&pa.dbg[CONV_DBG_PROD_WAIT_EMPTY], (unsigned long long)t_wait);
         atomicAdd(&pa.dbg[CONV_DBG_PROD_TOTAL], (unsigned long long)(clk() - t_begin));
@@ -452,9 +465,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 1 && rank == 0) {
     // ------------------------------ MMA issuer (pair: leader CTA only) ------------------------------
-    // One elected thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions; keeping the
-    // other 31 lanes out of the loop removes the per-step elect / reconvergence overhead).
-    if (elect_one()) {
+    // solo: one elected thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions);
+    // otherwise all lanes walk the loop and elect an issuer per stage.
+    auto issue_loop = [&](const bool solo, auto ks_tag) {
+      constexpr int KS = decltype(ks_tag)::value;
       constexpr uint32_t idesc = PAIR ? make_idesc_m<BN, 256>() : make_idesc<BN>();
       int stage = 0;
       uint32_t phase = 0;
@@ -477,44 +491,59 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (dbg) t_tmem += clk() - t0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb0 = 0; kb0 < num_k; kb0 += ksub) {
-          const int cnt = (num_k - kb0 < ksub) ? num_k - kb0 : ksub;
+        for (int kb0 = 0; kb0 < num_k; kb0 += (KS ? KS : ksub)) {
+          const int cnt = KS ? KS : ((num_k - kb0 < ksub) ? num_k - kb0 : ksub);
           t0 = dbg ? clk() : 0;
           mbar_wait(&full_bar[stage], phase);
           if (dbg) t_full += clk() - t0;
           tc_fence_after();
-          const uint32_t st_base = stages_addr + (uint32_t)(stage * stage_bytes);
-          if (do_mma) {
-            for (int j = 0; j < cnt; ++j) {
-              const uint32_t sa = st_base + (uint32_t)(j * sub_bytes);
-              const uint64_t da = make_kmajor_desc<BK>(sa);
-              const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)((kb0 + j) * B_BYTES) : sa + A_BYTES);
+          if (solo || elect_one()) {
+            const uint32_t st_base = stages_addr + (uint32_t)(stage * stage_bytes);
+            if (do_mma) {
+              for (int j = 0; j < cnt; ++j) {
+                const uint32_t sa = st_base + (uint32_t)(j * sub_bytes);
+                const uint64_t da = make_kmajor_desc<BK>(sa);
+                const uint64_t db = make_kmajor_desc<BK>(bstat ? b_stat_addr + (uint32_t)((kb0 + j) * B_BYTES) : sa + A_BYTES);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
-                const uint32_t accum = ((kb0 + j) | k) != 0 ? 1u : 0u;
-                if (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
-                else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+                for (int k = 0; k < BK / 16; ++k) {
+                  // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
+                  const uint32_t accum = ((kb0 + j) | k) != 0 ? 1u : 0u;
+                  if (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+                  else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
+                }
               }
             }
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage], 3);                          // frees this smem stage in both CTAs
+              if (kb0 + cnt == num_k) umma_commit_pair(&tmem_full_bar[acc], 3);  // accumulator complete
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb0 + cnt == num_k) umma_commit(&tmem_full_bar[acc]);
+            }
           }
-          if (PAIR) {
-            umma_commit_pair(&empty_bar[stage], 3);                          // frees this smem stage in both CTAs
-            if (kb0 + cnt == num_k) umma_commit_pair(&tmem_full_bar[acc], 3);  // accumulator complete
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb0 + cnt == num_k) umma_commit(&tmem_full_bar[acc]);
-          }
+          if (!solo) __syncwarp();
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (dbg) {
+      if (dbg && (solo || lane == 0)) {
         atomicAdd(&pa.dbg[CONV_DBG_MMA_WAIT_FULL], (unsigned long long)t_full);
         atomicAdd(&pa.dbg[CONV_DBG_MMA_WAIT_TMEM], (unsigned long long)t_tmem);
         atomicAdd(&pa.dbg[CONV_DBG_MMA_TOTAL], (unsigned long long)(clk() - t_begin));
       }
+    };
+    auto issue = [&](const bool solo) {
+      if (ksub == 1) issue_loop(solo, std::integral_constant<int, 1>{});
+      else if (ksub == 2 && num_k % 2 == 0) issue_loop(solo, std::integral_constant<int, 2>{});
+      else if (ksub == 3 && num_k % 3 == 0) issue_loop(solo, std::integral_constant<int, 3>{});
+      else if (ksub == 9 && num_k % 9 == 0) issue_loop(solo, std::integral_constant<int, 9>{});
+      else issue_loop(solo, std::integral_constant<int, 0>{});
+    };
+    if (pa.solo_issue) {
+      if (elect_one()) issue(true);
+      __syncwarp();
+    } else {
+      issue(false);
     }
-    __syncwarp();
   } else if (warp >= 2) {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;

@@ -430,6 +430,7 @@ struct yb_engine {
   bool tma_epilogue = true;
   bool cta_pairs = true;
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
+  int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
   int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
   unsigned long long* dbg_counters = nullptr;   // device [CONV_DBG_COUNT] cycle counters while "cycles" is switched on
   int num_sms = 148;
@@ -481,6 +482,7 @@ struct LaunchEnv {
   bool allow_bstat, allow_tma_epi, pdl;
   int ablate;
   unsigned long long* dbg;
+  int solo_issue;
 };
 
 // Resolves a ConvCfg into the launch parameters of conv_tc_persist_kernel<BN,BK,PAIR> and launches it.
@@ -497,6 +499,7 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
   pa.n_tiles = tiles_m * pa.n_tiles_n;
   pa.ablate = env.ablate;
   pa.dbg = env.dbg;
+  pa.solo_issue = env.solo_issue;
   // TMA-store epilogue.  Heuristic: the staging buffers cost one pipeline stage at BN=256, worth it while the epilogue
   // is the long pole (K <= 1152) or the pair kernel halves the operand bytes anyway.
   bool tma_epi = env.allow_tma_epi && op.tma_epi && cfg.tma_epi != 0;
@@ -627,7 +630,7 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate, e->dbg_counters};
+      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate, e->dbg_counters, e->solo_issue};
       ConvCfg cfg = cfg_override ? *cfg_override : op.cfg;
       if (cfg.pair && ceil_div(a.M, 128) < 2) cfg.pair = 0;          // a batch too small to form a pair of M tiles
       YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
@@ -1573,6 +1576,7 @@ int yb_engine_set_option(yb_engine* e, const char* name, int value) {
   if (!e || !name) return fail(YB_ERR_INVALID, "yb_engine_set_option: bad argument");
   if (!strcmp(name, "pdl")) e->pdl = value != 0;
   else if (!strcmp(name, "ablate")) e->ablate = value & 15;
+  else if (!strcmp(name, "solo_issue")) e->solo_issue = value != 0;
   else if (!strcmp(name, "cycles")) {       // in-kernel cycle counters of the conv roles (read with yb_engine_read_cycles)
     YB_TRY(set_device(e->device));
     if (value && !e->dbg_counters) {

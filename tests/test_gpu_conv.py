@@ -93,6 +93,28 @@ def test_v3_416_full_size_layers(keep_all):
     eng.close()
 
 
+def test_v3_608_config4_output_and_batch_consistency():
+    """BASELINE config 4: the 608 x 608 network (R = 22,743 rows).  Output vs the fp32 oracle for one image, and a
+    batch of 6 through an autotuned engine must reproduce that image bit for bit at every batch position."""
+    shape = (608, 608, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=2)
+    x = synth.images(1, 608, 608, seed=11)
+    eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 6, stream)
+    eng.forward(x)
+    y = eng.read_output()
+    assert y.shape == (1, 22743, 85)
+    assert helpers.rel_err(y, convstack.forward(topo, stream, x)) <= TOL
+    eng.autotune(6, reps=2)
+    xb = np.concatenate([x] * 6, 0)
+    eng.forward(xb)
+    yb_ = eng.read_output()
+    for i in range(6):
+        assert np.array_equal(yb_[i], y[0]), i
+    dets = eng.detect(0.5, 0.6)
+    assert all(np.array_equal(d, dets[0]) for d in dets)
+    eng.close()
+
+
 def test_v2_416_coco_and_voc():
     for nc, anchors in ((80, helpers.V2_ANCHORS_COCO), (20, helpers.V2_ANCHORS_VOC)):
         shape = (416, 416, 3)
