@@ -1,4 +1,13 @@
-"""CLI with the reference's flags (launcher.py): --config <ini> --mode test|anchor.  train is out of scope."""
+"""Command line of the B200 YOLO path, flag-compatible with the reference's launcher.py:
+
+    python launcher.py --config config/yolo_3.ini --mode test      # detect, draw, save (Yolo.test)
+    python launcher.py --config config/yolo_2.ini --mode anchor    # k-means anchors from VOC annotations (v2)
+
+The .ini layout is the reference's: a [COMMON] section merged into the section of the selected mode; keys ending in
+_dir / _path are resolved relative to the .ini file, `anchors` and `class_names` are Python literals.  `--section`
+selects another TEST-like section (config/yolo_2.ini ships [TEST] for VOC and [TEST_COCO]).  Training is not part of
+this package.
+"""
 import argparse
 import ast
 import configparser
@@ -6,36 +15,44 @@ import os
 
 from tensorflow_yolo_b200.net.yolo import YoloV2, YoloV3
 
+VERSIONS = {"v2": YoloV2, "v3": YoloV3}
+LITERAL_KEYS = ("anchors", "class_names")
+PATH_SUFFIXES = ("_dir", "_path")
 
-def _update_configs(configs, configs_path):
-    base_dir = os.path.dirname(os.path.abspath(configs_path))
-    for k, v in configs.items():
-        if (k.endswith("_dir") or k.endswith("_path")) and not os.path.isabs(v):
-            configs[k] = os.path.join(base_dir, v)
-        if k in ("anchors", "class_names"):
-            configs[k] = ast.literal_eval(v)
-    return configs
+
+def _resolve(section, ini_path):
+    """Applies the reference's two conventions to one section (launcher.py:5-12 there)."""
+    root = os.path.dirname(os.path.abspath(ini_path))
+    out = {}
+    for key, value in section.items():
+        if key.endswith(PATH_SUFFIXES) and not os.path.isabs(value):
+            value = os.path.join(root, value)
+        elif key in LITERAL_KEYS:
+            value = ast.literal_eval(value)
+        out[key] = value
+    return out
 
 
 def load_config(path):
-    cfg = configparser.ConfigParser()
-    if not cfg.read(path):
+    parser = configparser.ConfigParser()
+    if not parser.read(path):
         raise FileNotFoundError(path)
-    return {s: _update_configs(dict(cfg.items(s)), path) for s in cfg.sections()}
+    return {name: _resolve(dict(parser.items(name)), path) for name in parser.sections()}
+
+
+def _params(cfg, section):
+    return dict(cfg[section], **cfg["COMMON"])
 
 
 def _main(cfg, mode, test_section="TEST"):
     version = cfg["COMMON"]["version"]
-    if version == "v2":
-        yolo = YoloV2()
-    elif version == "v3":
-        yolo = YoloV3()
-    else:
+    if version not in VERSIONS:
         raise ValueError("Unsupported version: {}".format(version))
+    yolo = VERSIONS[version]()
     if mode == "test":
-        return yolo.test({**cfg[test_section], **cfg["COMMON"]})
+        return yolo.test(_params(cfg, test_section))
     if mode == "anchor":
-        anchors, class_names = yolo.generate_anchors({**cfg["ANCHOR"], **cfg["COMMON"]})
+        anchors, class_names = yolo.generate_anchors(_params(cfg, "ANCHOR"))
         print("Anchors: ")
         print("\t{}".format(anchors))
         print("Class names: ")
@@ -46,11 +63,15 @@ def _main(cfg, mode, test_section="TEST"):
     raise ValueError("Unsupported mode: {}".format(mode))
 
 
+def main(argv=None):
+    here = os.path.dirname(os.path.abspath(__file__))
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--config", default=os.path.join(here, "config", "yolo_3.ini"), help="Path to configuration file")
+    ap.add_argument("--mode", default="test", help="Mode: (test|anchor)")
+    ap.add_argument("--section", default="TEST", help="ini section holding the TEST parameters")
+    args = ap.parse_args(argv)
+    return _main(load_config(args.config), args.mode.lower(), args.section)
+
+
 if __name__ == "__main__":
-    args = argparse.ArgumentParser()
-    args.add_argument("--config", dest="config", help="Path to configuration file",
-                      default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "config", "yolo_3.ini"))
-    args.add_argument("--mode", dest="mode", help="Mode: (test|anchor)", default="test")
-    args.add_argument("--section", dest="section", help="ini section holding the TEST parameters", default="TEST")
-    c = args.parse_args()
-    _main(load_config(c.config), c.mode.lower(), c.section)
+    main()
