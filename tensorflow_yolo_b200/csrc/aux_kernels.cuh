@@ -148,6 +148,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 constexpr int FIRST_ROWS = 8;     // output rows per block (one per warp)
+// shared-memory elements per staged row: 4 leading (1 unused + left halo), W*3 image, 8 trailing (right halo + padded k)
+#define FIRST_ROW_ELEMS(W) ((W) * 3 + 12)
 
 template <bool U8>
 __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
@@ -156,7 +158,9 @@ __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, co
   // right (rows outside the image are zero), so the gather below needs no bounds checks at all.
   extern __shared__ __align__(16) uint16_t s_in[];
   const int W = in.W, H = in.H;
-  const int row_elems = (W + 2) * 3 + 2;             // +2: the padded k columns read one element past the halo
+  // row layout: [1 unused][left halo pixel: 3][W*3 image elements][right halo pixel: 3][padding]; the image data starts
+  // at element 4 (8 bytes) so that four converted elements go out as one 8-byte store
+  const int row_elems = FIRST_ROW_ELEMS(W);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int c0 = blockIdx.y * 32;
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, co
     const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
     const int kk = k < K ? k : 0;                    // padded columns read a valid element; their weights are zero
     const int tap = kk / 3, ci = kk - tap * 3;
-    soff[j] = (tap / 3) * row_elems + (tap % 3) * 3 + ci;
+    soff[j] = 1 + (tap / 3) * row_elems + (tap % 3) * 3 + ci;
   }
   // B fragments with permuted columns: column g of n-tile nt holds channel c0 + (g/2)*8 + 2*nt + (g&1)
   uint32_t bf[2][4][2];
@@ -195,22 +199,28 @@ __global__ void __launch_bounds__(256) conv_first_mma_kernel(const InView in, co
     const int img = grp / groups_per_img;
     const int y0 = (grp - img * groups_per_img) * FIRST_ROWS;
     __syncthreads();                                 // previous group's gathers are done
-    // ---- stage rows y0-1 .. y0+FIRST_ROWS (coalesced), converting to bf16 ----
-    for (int r = 0; r < FIRST_ROWS + 2; ++r) {
+    // ---- stage rows y0-1 .. y0+FIRST_ROWS, converting to bf16: four elements per thread and step (16-byte loads
+    // of float input, 4-byte loads of uint8 input), all loads of a thread independent of each other ----
+    const int quads = row_in >> 2;                   // host guarantees row_in % 4 == 0
+    for (int i = threadIdx.x; i < (FIRST_ROWS + 2) * quads; i += 256) {
+      const int r = i / quads, q = i - r * quads;
       const int y = y0 - 1 + r;
-      uint16_t* dst = s_in + r * row_elems;
-      const bool inside = (unsigned)y < (unsigned)H;
-      const long long src = ((long long)img * H + y) * row_in;
-      for (int i = threadIdx.x; i < row_elems; i += 256) {
-        const int e = i - 3;                         // element index inside the image row
-        float v = 0.0f;
-        if (inside && e >= 0 && e < row_in) {
-          if (U8) v = u8_lut[reinterpret_cast<const uint8_t*>(in.ptr)[src + e]];
-          else v = __ldg(reinterpret_cast<const float*>(in.ptr) + src + e);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)y < (unsigned)H) {
+        const long long src = ((long long)img * H + y) * row_in + 4 * q;
+        if (U8) {
+          const uint32_t w4 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(in.ptr) + src));
+          v = make_float4(u8_lut[w4 & 0xFFu], u8_lut[(w4 >> 8) & 0xFFu], u8_lut[(w4 >> 16) & 0xFFu], u8_lut[w4 >> 24]);
+        } else {
+          v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in.ptr) + src));
         }
-        __nv_bfloat16 b = __float2bfloat16_rn(v);
-        dst[i] = *reinterpret_cast<uint16_t*>(&b);
       }
+      *reinterpret_cast<uint2*>(s_in + r * row_elems + 4 + 4 * q) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    // halo pixels and the tail padding are zero (written once per group: the staging above never touches them)
+    for (int i = threadIdx.x; i < (FIRST_ROWS + 2) * 12; i += 256) {
+      const int r = i / 12, e = i - r * 12;
+      s_in[r * row_elems + (e < 4 ? e : 4 + row_in + (e - 4))] = 0;
     }
     __syncthreads();
     const int y = y0 + warp;

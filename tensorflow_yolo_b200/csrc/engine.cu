@@ -636,22 +636,30 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
       YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
+      const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(op.in.w) * 2;
       const bool mma_ok = op.ksize == 3 && op.cin == 3 && op.stride == 1 && op.cout % 32 == 0 && !op.out.f32 && !op.has_res &&
                           op.out_mode == OUT_PLAIN && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
-                          op.in.ld == 3 && (FIRST_ROWS + 2) * ((op.in.w + 2) * 3 + 2) * 2 <= 200 * 1024;
+                          op.in.ld == 3 && (op.in.w * 3) % 4 == 0 && smem_first <= 200 * 1024;
       if (mma_ok) {
         const int groups = n * ceil_div(op.Ho, FIRST_ROWS);     // stride 1: output rows == input rows
-        const int smem_first = (FIRST_ROWS + 2) * ((op.in.w + 2) * 3 + 2) * 2;
-        dim3 grid(std::min(groups, e->num_sms * 4), op.cout / 32);
-        if (u8) {
-          YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_first));
-          conv_first_mma_kernel<true><<<grid, 256, smem_first, st>>>(in, op.d_wt32, a, e->d_u8_lut, groups);
-        } else {
-          YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_first));
-          conv_first_mma_kernel<false><<<grid, 256, smem_first, st>>>(in, op.d_wt32, a, e->d_u8_lut, groups);
-        }
-        YB_CUDA(cudaGetLastError());
-        return YB_OK;
+        auto launch = [&](auto kern) -> int {
+          static int resident[2][64] = {{0}};                   // per kernel variant and device: co-resident blocks per SM
+          int& res = resident[u8 ? 1 : 0][e->device < 64 ? e->device : 63];
+          if (res == 0) {
+            YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kern, 256, smem_first));
+            if (res < 1) res = 1;
+          }
+          // exactly one resident wave: the blocks walk the row groups with a grid stride, a partial second wave
+          // would run at a fraction of the occupancy
+          dim3 grid(std::min(groups, e->num_sms * res / std::max(1, op.cout / 32)), op.cout / 32);
+          if (grid.x < 1) grid.x = 1;
+          kern<<<grid, 256, smem_first, st>>>(in, op.d_wt32, a, e->d_u8_lut, groups);
+          YB_CUDA(cudaGetLastError());
+          return YB_OK;
+        };
+        if (u8) return launch(conv_first_mma_kernel<true>);
+        return launch(conv_first_mma_kernel<false>);
       }
       const int smem = a.taps * op.cin * 32 * 4;
       dim3 grid(ceil_div(a.M, 128), ceil_div(op.cout, 32));
