@@ -579,10 +579,95 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       s_karea[pos] = sarea[b0 + tid];
     }
     __syncthreads();
-    // 4c. every kept box of this block suppresses all later boxes.  Two passes per later box j so that the lanes of a
-    // warp stay together: first the cheap float test against all kept boxes (bit q of a mask = kept box q may overlap
-    // j), then the exact decision only for the boxes in the mask -- a few per j even in the dense case.
-    if (nkept > 0) {
+    // 4c. every kept box of this block suppresses all later boxes.  Per later box j: (1) the cheap float test against
+    // all kept boxes gives a 64-bit mask of those that may overlap j; (2) only those pairs get a decision.
+    if (nkept > 0 && use_f32) {
+      // Flattened variant (float64 boxes, the engine's regime): the (j, kept box) pairs of the warp's 32 boxes are
+      // written to a per-warp queue (in the shared memory the sort keys no longer need) and evaluated 32 at a time, so
+      // every lane works whatever the distribution of candidates over the lanes; the j box travels by shuffle.
+      unsigned short* wq = reinterpret_cast<unsigned short*>(s_keys) + (tid >> 5) * 2048;
+      const int lane = tid & 31;
+      for (int j0 = b0 + NMS_BLOCK + (tid & ~31); j0 < K; j0 += NMS_THREADS) {
+        const int j = j0 + lane;
+        const unsigned char fj = (j < K) ? flags[j] : (unsigned char)1;
+        const bool live = !(fj & 1);
+        const int cj = (per_class && live) ? scls[j] : 0;
+        float4 oj = make_float4(0.f, 0.f, 0.f, 0.f), ij = oj;
+        float2 aj = make_float2(0.f, 0.f);
+        unsigned long long todo = 0ull;
+        bool sup = false;
+        if (live && !(fj & 4)) {
+          oj = sf4[j]; ij = sf4i[j]; aj = sarea[j];
+          unsigned lo = 0xffffffffu, hi = 0xffffffffu;
+          if (skip_disjoint) {
+            lo = hi = 0u;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float4 fa = s_kf4[q], fb = s_kf4[q + 32];      // entries >= nkept are stale but masked off below
+              lo |= surely_disjoint(fa, oj) ? 0u : (1u << q);
+              hi |= surely_disjoint(fb, oj) ? 0u : (1u << q);
+            }
+          }
+          todo = ((unsigned long long)hi << 32) | lo;
+          if (nkept < 64) todo &= (1ull << nkept) - 1ull;
+        } else if (live) {
+          // a non-finite box j (rare): exact numpy-semantics IoU against every kept box, on this lane alone
+          const BoxC<T> bj = sb[j];
+          for (int q = 0; q < nkept && !sup; ++q) {
+            if (per_class && s_kcls[q] != cj) continue;
+            const T v = iou_ref<T, true>(s_kbox[q], bj);
+            sup = per_class ? (v > thr) : (v >= thr);
+          }
+        }
+        // exclusive scan of the candidate counts over the warp
+        const int cnt = __popcll(todo);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = incl - cnt;
+        while (todo) {
+          const int q = __ffsll((long long)todo) - 1;
+          todo &= todo - 1;
+          wq[pos++] = (unsigned short)((lane << 6) | q);
+        }
+        __syncwarp();
+        unsigned supmask = 0u;
+        for (int s0 = 0; s0 < total; s0 += 32) {
+          const bool valid = s0 + lane < total;
+          const unsigned e = valid ? wq[s0 + lane] : 0u;
+          const int l = (int)(e >> 6), q = (int)(e & 63u);
+          float4 o2, i2;
+          float2 a2;
+          o2.x = __shfl_sync(0xffffffffu, oj.x, l); o2.y = __shfl_sync(0xffffffffu, oj.y, l);
+          o2.z = __shfl_sync(0xffffffffu, oj.z, l); o2.w = __shfl_sync(0xffffffffu, oj.w, l);
+          i2.x = __shfl_sync(0xffffffffu, ij.x, l); i2.y = __shfl_sync(0xffffffffu, ij.y, l);
+          i2.z = __shfl_sync(0xffffffffu, ij.z, l); i2.w = __shfl_sync(0xffffffffu, ij.w, l);
+          a2.x = __shfl_sync(0xffffffffu, aj.x, l); a2.y = __shfl_sync(0xffffffffu, aj.y, l);
+          const int c2 = per_class ? __shfl_sync(0xffffffffu, cj, l) : 0;
+          bool hit = false;
+          if (valid && !(per_class && s_kcls[q] != c2)) {
+            const int d = s_knf[q] ? 0 : decide_f32(s_kf4[q], s_kf4i[q], s_karea[q], o2, i2, a2, thr_dn, thr_up);
+            hit = d > 0;
+            if (d == 0) {                       // too close to the threshold (or a non-finite kept box): exact float64
+              const BoxC<T> bl = sb[j0 + l];
+              if (s_knf[q]) {
+                const T v = iou_ref<T, true>(s_kbox[q], bl);
+                hit = per_class ? (v > thr) : (v >= thr);
+              } else {
+                hit = suppresses_finite<T>(s_kbox[q], bl, thr, per_class);
+              }
+            }
+          }
+          supmask |= __reduce_or_sync(0xffffffffu, hit ? (1u << l) : 0u);
+        }
+        if (live && (sup || ((supmask >> lane) & 1u))) flags[j] = fj | 1;
+        __syncwarp();                           // the queue is rewritten by the next group of 32 boxes
+      }
+    } else if (nkept > 0) {
       for (int j = b0 + NMS_BLOCK + tid; j < K; j += NMS_THREADS) {
         const unsigned char fj = flags[j];
         if (fj & 1) continue;
@@ -602,22 +687,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         if (nkept < 64) todo &= (1ull << nkept) - 1ull;
         if (todo == 0ull) continue;
         bool sup = false;
-        if (use_f32 && !(fj & 4)) {
-          // float interval pass over the boxes that may overlap: decides all but near-threshold pairs
-          const float4 oj = sf4[j], ij = sf4i[j];
-          const float2 aj = sarea[j];
-          unsigned long long unsure = 0ull;
-          while (todo && !sup) {
-            const int q = __ffsll((long long)todo) - 1;
-            todo &= todo - 1;
-            if (per_class && s_kcls[q] != cj) continue;
-            if (s_knf[q]) { unsure |= 1ull << q; continue; }
-            const int d = decide_f32(s_kf4[q], s_kf4i[q], s_karea[q], oj, ij, aj, thr_dn, thr_up);
-            sup = d > 0;
-            if (d == 0) unsure |= 1ull << q;
-          }
-          todo = sup ? 0ull : unsure;
-        }
         if (todo) {
           const BoxC<T> bj = sb[j];
           while (todo && !sup) {
@@ -655,7 +724,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
     __syncthreads();
     if (tid < 32) {
-      int wsum = s_scan[tid];
+      int wsum = (tid < NMS_THREADS / 32) ? s_scan[tid] : 0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, wsum, d);
@@ -666,7 +735,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     __syncthreads();
     const int warp_off = (tid >> 5) ? s_scan[(tid >> 5) - 1] : 0;
     const int pos = s_running + warp_off + incl - keep;
-    const int chunk_total = s_scan[31];
+    const int chunk_total = s_scan[31];       // inclusive sum over all warps (entries beyond the last warp repeat it)
     __syncthreads();        // everyone has read order[i] / s_running / s_scan
     if (keep) order[pos] = row;   // pos <= i, and all reads of this chunk are done
     if (tid == 0) s_running += chunk_total;
