@@ -79,7 +79,14 @@ class NetworkState(object):
                                      max_batch=self.max_batch, device=self.device)
         if self.pending_stream is not None:
             self.engine.load_weights(self.pending_stream)
+            self.tune()
         return self.engine
+
+    def tune(self):
+        """Per-layer launch configurations measured on the device for this engine's batch size (about a second, once
+        per engine; results are bit-identical with or without it).  YB_AUTOTUNE=0 keeps the heuristic."""
+        if self.engine is not None and os.environ.get("YB_AUTOTUNE", "1") != "0":
+            self.engine.autotune(self.max_batch, reps=3)
 
 
 def state_of(layers):
@@ -99,6 +106,7 @@ class _AssignWeights(object):
         self.state.pending_stream = self.stream
         if self.state.engine is not None:
             self.state.engine.load_weights(self.stream)
+            self.state.tune()
 
 
 def load_weights(layers, weights):
