@@ -33,6 +33,18 @@ OBJ_BIAS = -3.4                              # synthetic head bias: ~tens of can
 METRIC = "YOLOv3-416 images/sec (conv+decode+NMS)"
 
 
+def workload_name(args):
+    if args.net == "v3":
+        return "YOLOv3-{} COCO-80 (Darknet-53, 3 scales, 9 anchors)".format(args.size)
+    return "YOLOv2-{} {} (Darknet-19, 5 anchors)".format(args.size, "VOC-20" if args.net == "v2voc" else "COCO-80")
+
+
+def metric_name(args):
+    if args.net == "v3" and args.size == 416:
+        return METRIC
+    return "{}-{} images/sec (conv+decode+NMS)".format("YOLOv3" if args.net == "v3" else "YOLOv2", args.size)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -81,13 +93,27 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_network(size):
+V2_ANCHORS = {"v2voc": [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071],
+              "v2coco": [0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828]}
+
+
+def net_classes(net_name):
+    return 20 if net_name == "v2voc" else NUM_CLASSES
+
+
+def build_network(size, net_name="v3"):
+    """v3 (the headline workload, BASELINE configs 3/4) or YOLOv2 (configs 1/2: --net v2voc / v2coco)."""
     from tensorflow_yolo_b200 import synth
-    from tensorflow_yolo_b200.net import v3 as pv3
+    from tensorflow_yolo_b200.net import v2 as pv2, v3 as pv3
     shape = (size, size, 3)
-    net = pv3.create_network(np.reshape(V3_ANCHORS, [-1, 2]), ["c%d" % i for i in range(NUM_CLASSES)], False, input_shape=shape)
+    nc = net_classes(net_name)
+    names = ["c%d" % i for i in range(nc)]
+    if net_name == "v3":
+        net = pv3.create_network(np.reshape(V3_ANCHORS, [-1, 2]), names, False, input_shape=shape)
+    else:
+        net = pv2.create_full_network(np.reshape(V2_ANCHORS[net_name], [-1, 2]), names, False, input_shape=shape)
     state = net[0]._yb_state
-    stream = synth.weight_stream(state.graph.specs, seed=2, num_classes=NUM_CLASSES, obj_bias=OBJ_BIAS)
+    stream = synth.weight_stream(state.graph.specs, seed=2, num_classes=nc, obj_bias=OBJ_BIAS if net_name == "v3" else 1.0)
     return net, state, stream, shape
 
 
@@ -95,10 +121,12 @@ def cpu_pipeline(topo, stream, geo, images):
     """The oracle port of the whole path on the host: torch-CPU fp32 conv stack (all threads) + numpy decode/NMS."""
     from oracle import convstack, postprocess
     out = convstack.forward(topo, stream, images)
+    if isinstance(geo, tuple) and geo and geo[0] == "v2":
+        return postprocess.find_bounding_boxes_v2(out, geo[1], geo[2], THRESHOLD, IOU_THRESHOLD)
     return postprocess.find_bounding_boxes_v3(out, geo, THRESHOLD, IOU_THRESHOLD)
 
 
-def cpu_setup(size):
+def cpu_setup(size, net_name="v3"):
     import torch
     from oracle import convstack
     # all host threads the process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
@@ -106,9 +134,14 @@ def cpu_setup(size):
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, RuntimeError):
         torch.set_num_threads(os.cpu_count() or 1)
-    net, state, stream, shape = build_network(size)
-    topo = convstack.topology_v3(NUM_CLASSES, np.reshape(V3_ANCHORS, [-1, 2]), shape)
-    geo = convstack.yolo_geometry(topo, shape)
+    net, state, stream, shape = build_network(size, net_name)
+    if net_name == "v3":
+        topo = convstack.topology_v3(NUM_CLASSES, np.reshape(V3_ANCHORS, [-1, 2]), shape)
+        geo = convstack.yolo_geometry(topo, shape)
+    else:
+        anchors = np.reshape(V2_ANCHORS[net_name], [-1, 2])
+        topo = convstack.topology_v2(net_classes(net_name), len(anchors), shape)
+        geo = ("v2", anchors, net_classes(net_name))
     return topo, stream, geo, torch.get_num_threads()
 
 
@@ -119,7 +152,7 @@ def run_reference(args):
         return None
     from tensorflow_yolo_b200 import synth
     sample = args.cpu_images
-    topo, stream, geo, threads = cpu_setup(args.size)
+    topo, stream, geo, threads = cpu_setup(args.size, args.net)
     images = synth.images(sample, args.size, args.size, seed=1)
     for _ in range(args.warmup):
         cpu_pipeline(topo, stream, geo, images)
@@ -130,10 +163,10 @@ def run_reference(args):
     value = sample * args.steps / dt
     what = "{} image(s) per step of the same synthetic 416 workload".format(sample)
     return ({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLOv3-{} COCO-80 conv stack + decode + NMS, CPU oracle port".format(args.size),
+        "config": {"workload": "{} conv stack + decode + NMS, CPU oracle port".format(workload_name(args)),
                    "images_per_step": sample, "threshold": THRESHOLD, "iou_threshold": IOU_THRESHOLD},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -166,8 +199,9 @@ def run_ours(args):
         return float(t.item())
 
     B, K, W = args.batch, args.steps, args.warmup
-    net, state, stream, shape = build_network(args.size)
-    eng = yb.Engine(state.plan(), shape, NUM_CLASSES, yb.YB_DECODE_V3, max_batch=B, device=local)
+    net, state, stream, shape = build_network(args.size, args.net)
+    eng = yb.Engine(state.plan(), shape, net_classes(args.net), yb.YB_DECODE_V3 if args.net == "v3" else yb.YB_DECODE_V2,
+                    max_batch=B, device=local)
     eng.load_weights(stream)
     flops_img = yplan.conv_flops(state.graph.specs)
     tune = None
@@ -306,7 +340,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from tensorflow_yolo_b200 import synth
-        topo, cstream, geo, threads = cpu_setup(args.size)
+        topo, cstream, geo, threads = cpu_setup(args.size, args.net)
         imgs = synth.images(args.cpu_images, args.size, args.size, seed=1)
         cpu_pipeline(topo, cstream, geo, imgs[:1])
         t0 = time.perf_counter()
@@ -319,11 +353,11 @@ def run_ours(args):
                "sample": "{} x {} synthetic 416 images through the oracle port (torch-CPU fp32 conv stack on all threads + numpy "
                          "decode/NMS; TensorFlow itself is not installable)".format(reps, args.cpu_images)}
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "YOLOv3-{} COCO-80 (Darknet-53, 3 scales, 9 anchors): 75 convs + decode + NMS, random-init darknet "
-                               ".weights".format(args.size),
+        "config": {"workload": "{}: {} convs + decode + NMS, random-init darknet .weights".format(
+                       workload_name(args), sum(1 for sp in state.graph.specs if sp.kind == yplan.KIND_CONV)),
                    "batch_per_gpu": B, "global_batch": B * world, "threshold": THRESHOLD, "iou_threshold": IOU_THRESHOLD,
                    "parallelism": "batch sharded over {} GPU(s), no collective".format(world),
                    "l2": "no flush needed: inputs ({} MB) and activations (>1 GB per step) exceed the 126 MB L2".format(
@@ -351,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--net", default="v3", choices=["v3", "v2voc", "v2coco"],
+                    help="network: v3 (headline, BASELINE configs 3/4) or YOLOv2 VOC/COCO (configs 2/1)")
     ap.add_argument("--max-per-image", type=int, default=256)
     ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline pass")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-clock budget of the cpu_baseline leg")

@@ -214,3 +214,27 @@ def test_device_resident_head_and_batch_limits():
         assert np.array_equal(x[:7], y)
     with pytest.raises(Exception):
         post.run(np.concatenate([head, head]), 0.5, 0.6)          # batch 4 > max_batch 2
+
+
+def test_no_candidates_and_single_candidate():
+    """Empty inputs of the domain: an image without any candidate (the reference returns [] for it, net/base.py:196-197)
+    next to images with one and with many candidates, in one batch."""
+    topo = convstack.topology_v3(80, np.reshape(helpers.V3_ANCHORS, [-1, 2]), (416, 416, 3))
+    geo = convstack.yolo_geometry(topo, (416, 416, 3))
+    rows = sum(h * w * b for h, w, b, a in geo)
+    head = np.random.RandomState(5).standard_normal((3, rows, 85)).astype(np.float32)
+    head[0, :, 4] = -20.0                    # no row reaches the threshold
+    head[1, :, 4] = -20.0
+    head[1, 1234, 4] = 3.0                   # exactly one candidate
+    post = engine.PostProcessor([(h, w, a) for h, w, b, a in geo], 80, engine.YB_DECODE_V3, max_batch=3)
+    kept = post.run(head, 0.5, 0.6)
+    assert len(kept[0]) == 0 and post.last_candidates[0] == 0
+    assert len(kept[1]) == 1 and kept[1][0]["row"] == 1234 and post.last_candidates[1] == 1
+    ref = postprocess.find_bounding_boxes_v3(head[:2], geo, 0.5, 0.6)
+    for i in range(2):
+        assert np.array_equal(kept[i]["row"], ref[i]["row"])
+    # the dense image: the candidate set is exact (sigmoid(t) >= 0.5 <=> t >= 0); its kept list is covered by the
+    # bit-identical NMS tests above, which start from the reference's own decoded boxes
+    assert post.last_candidates[2] == int((head[2, :, 4] >= 0).sum()) and 0 < len(kept[2]) <= post.last_candidates[2]
+    # a threshold nothing can reach empties the whole batch
+    assert all(len(k) == 0 for k in post.run(head, 1.5, 0.6))
