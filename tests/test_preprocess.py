@@ -49,6 +49,26 @@ def test_oracle_matches_the_reference_preprocess_image(tmp_path):
         assert np.array_equal(want, got)
 
 
+def test_oracle_matches_committed_reference_fixture():
+    """tests/golden/preprocess.npz: outputs of the reference's preprocess_image made by oracle/make_golden_pre.py."""
+    g = helpers.golden("preprocess.npz")
+    for i in range(int(g["n_cases"])):
+        shape = tuple(int(v) for v in g["shape%d" % i])
+        got = opre.preprocess_u8(g["src%d" % i], shape)
+        assert got.shape == (shape[1], shape[0], 3) and np.array_equal(got, g["rgb%d" % i]), i
+        assert np.array_equal(opre.preprocess_image(g["src%d" % i], shape), g["rgb%d" % i] / 255.)
+
+
+@pytest.mark.gpu
+def test_gpu_resize_matches_committed_reference_fixture():
+    from tensorflow_yolo_b200 import engine
+    g = helpers.golden("preprocess.npz")
+    for i in range(int(g["n_cases"])):
+        shape = tuple(int(v) for v in g["shape%d" % i])
+        got = engine.resize_bgr2rgb([g["src%d" % i]], shape[1], shape[0])[0]        # dsize = (input_h, input_w): rows = input_w
+        assert np.array_equal(got, g["rgb%d" % i]), i
+
+
 @pytest.mark.gpu
 def test_gpu_resize_bit_exact_any_shape():
     from tensorflow_yolo_b200 import engine
