@@ -162,7 +162,7 @@ struct PostCtx {
   int* cls = nullptr;
   unsigned long long* keys = nullptr;
   void* sorted_boxes = nullptr;
-  float4 *sorted_f4 = nullptr, *sorted_f4i = nullptr;
+  float4 *sorted_f4 = nullptr, *sorted_f4s = nullptr, *sorted_f4i = nullptr;
   float2* sorted_area = nullptr;
   int* sorted_cls = nullptr;
   unsigned char* flags = nullptr;
@@ -182,6 +182,7 @@ struct PostCtx {
     if (rows_pow2 > NMS_SMEM_KEYS) YB_CUDA(cudaMalloc(&keys, (size_t)max_batch * rows_pow2 * 8));
     YB_CUDA(cudaMalloc(&sorted_boxes, nr * sizeof(BoxC<double>)));
     YB_CUDA(cudaMalloc(&sorted_f4, nr * sizeof(float4)));
+    YB_CUDA(cudaMalloc(&sorted_f4s, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_f4i, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_area, nr * sizeof(float2)));
     YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
@@ -193,7 +194,7 @@ struct PostCtx {
   }
   void release() {
     cudaFree(prob); cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(h); cudaFree(cls); cudaFree(keys);
-    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
+    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4s); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
     cudaFree(dets);
     for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
   }
@@ -230,7 +231,7 @@ struct PostCtx {
     memset(&a, 0, sizeof(a));
     a.rows = rows; a.per_class = per_class; a.thr = thr;
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
+    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
     a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;
     return a;
   }

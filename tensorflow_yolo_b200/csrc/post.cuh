@@ -373,6 +373,51 @@ __device__ __forceinline__ bool surely_disjoint(const float4& a, const float4& b
   return a.z <= b.x || b.z <= a.x || a.w <= b.y || b.w <= a.y;
 }
 
+// Necessary condition for "iou >= thr" between two REGULAR float64 boxes (finite, positive extent, area consistent with
+// the corners, extent not vanishing against the coordinates): with W = x2 - x1,
+//   inter <= min(area_p, area_q) (1 + 1e-9)  =>  union >= max(area_p, area_q) (1 - 1.1e-9)
+//   fl(inter / union) >= thr                =>  iw * ih >= thr * area_q (1 - 3e-9), and ih <= H_q
+//                                           =>  min(x2p, x2q) - max(x1p, x1q) >= thr * W_q (1 - 4e-9)
+// i.e. in each dimension either box must reach at least g = min(thr, 1) * (1 - 1e-6) * extent into the other one:
+// x2p >= x1q + g_q and x1p <= x2q - g_q (and the same with p and q swapped).  Every box therefore carries, next to
+// its outward-rounded corners, the corners "shrunk" by g (lower ones rounded down, upper ones rounded up, so the
+// shrunk box of a wide box is an inverted interval: the band the other box has to cover).  The 1e-6 margin covers the
+// float64 rounding of x1 + g (<= 1.2e-12 W for a regular box) for every thr >= 1e-2; below that g is 0 and the test is
+// plain disjointness.  Irregular boxes are flagged like non-finite ones and always take the exact path.
+__device__ __forceinline__ float4 shrunk_f4(double x1, double y1, double x2, double y2, double t) {
+  const double gx = __dmul_rn(t, __dsub_rn(x2, x1)), gy = __dmul_rn(t, __dsub_rn(y2, y1));
+  return make_float4(__double2float_rd(__dadd_rn(x1, gx)), __double2float_rd(__dadd_rn(y1, gy)),
+                     __double2float_ru(__dsub_rn(x2, gx)), __double2float_ru(__dsub_rn(y2, gy)));
+}
+__device__ __forceinline__ bool box_regular(double x1, double y1, double x2, double y2, double area) {
+  const double W = __dsub_rn(x2, x1), H = __dsub_rn(y2, y1), wh = __dmul_rn(W, H);
+  return W > 0.0 && H > 0.0 && area > 0.0 && fabs(wh - area) <= 1e-9 * area &&
+         W >= 1e-4 * fmax(fabs(x1), fabs(x2)) && H >= 1e-4 * fmax(fabs(y1), fabs(y2));
+}
+// true: box p (outward corners po, shrunk ps) and box q can certainly not reach iou >= thr
+__device__ __forceinline__ bool surely_below(const float4& qo, const float4& qs, const float4& po, const float4& ps) {
+  return (qs.z <= po.x) | (po.z <= qs.x) | (qs.w <= po.y) | (po.w <= qs.y) |
+         (qo.z <= ps.x) | (ps.z <= qo.x) | (qo.w <= ps.y) | (ps.w <= qo.y);
+}
+// mask |= bit unless surely_below(...): one chained-predicate compare per corner and one predicated OR (the C++ form
+// compiles to a compare plus a select per corner).  No operand is NaN (non-finite boxes never get here).
+__device__ __forceinline__ void or_unless_below(unsigned& mask, unsigned bit, const float4& qo, const float4& qs,
+                                                const float4& po, const float4& ps) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %2, %3;\n\t"
+      "setp.gt.and.f32 p, %4, %5, p;\n\t"
+      "setp.gt.and.f32 p, %6, %7, p;\n\t"
+      "setp.gt.and.f32 p, %8, %9, p;\n\t"
+      "setp.gt.and.f32 p, %10, %11, p;\n\t"
+      "setp.gt.and.f32 p, %12, %13, p;\n\t"
+      "setp.gt.and.f32 p, %14, %15, p;\n\t"
+      "setp.gt.and.f32 p, %16, %17, p;\n\t"
+      "@p or.b32 %0, %0, %1;\n\t}"
+      : "+r"(mask)
+      : "r"(bit), "f"(qs.z), "f"(po.x), "f"(po.z), "f"(qs.x), "f"(qs.w), "f"(po.y), "f"(po.w), "f"(qs.y),
+        "f"(qo.z), "f"(ps.x), "f"(ps.z), "f"(qo.x), "f"(qo.w), "f"(ps.y), "f"(ps.w), "f"(qo.y));
+}
+
 struct NmsArgs {
   int rows;             // R: dense rows per image (stride of every per-row array)
   int per_class;        // 0: reference (class-agnostic, >=); 1: per class, strict >
@@ -389,10 +434,11 @@ struct NmsArgs {
   int rows_pow2;
   void* sorted_boxes;   // BoxC<T> [n * rows]
   float4* sorted_f4;    // [n * rows]: outward-rounded float corners of the sorted boxes (disjointness prefilter)
+  float4* sorted_f4s;   // [n * rows]: shrunk float corners (see surely_below); == sorted_f4 when shrinking is off
   float4* sorted_f4i;   // [n * rows]: inward-rounded float corners          } float interval arithmetic,
   float2* sorted_area;  // [n * rows]: area rounded down / up to float       } see decide_f32
   int* sorted_cls;      // [n * rows]
-  unsigned char* flags; // [n * rows] bit0: removed, bit1: kept, bit2: non-finite box
+  unsigned char* flags; // [n * rows] bit0: removed, bit1: kept, bit2: non-finite or irregular box (exact path only)
   // outputs
   int* order;           // [n * rows]: kept rows in kept order
   int* n_keep;          // [n]
@@ -434,6 +480,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   __shared__ unsigned s_alive[2];
   __shared__ BoxC<T> s_kbox[NMS_BLOCK];        // the kept boxes of the current block, compacted
   __shared__ float4 s_kf4[NMS_BLOCK];
+  __shared__ float4 s_kf4s[NMS_BLOCK];
   __shared__ float4 s_kf4i[NMS_BLOCK];
   __shared__ float2 s_karea[NMS_BLOCK];
   __shared__ int s_kcls[NMS_BLOCK];
@@ -488,9 +535,20 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   __syncthreads();
   if (in_smem) bitonic_sort_desc(s_keys, P); else bitonic_sort_desc(gkeys, P);
 
+  const T thr = (T)a.thr;
+  const bool per_class = a.per_class != 0;
+  // iou == 0 never suppresses when thr > 0 (>=) / thr >= 0 (>): then surely disjoint pairs are skipped outright
+  const bool skip_disjoint = per_class ? (thr >= (T)0) : (thr > (T)0);
+  // float interval fast path (float64 boxes, positive threshold): bounds of thr (1 -+ 1e-6) rounded outwards
+  const bool use_f32 = sizeof(T) == 8 && a.thr > 1e-30 && a.thr < 1e30;
+  const float thr_dn = __double2float_rd(a.thr * 0.999999), thr_up = __double2float_ru(a.thr * 1.000001);
+  // shrink factor of the prefilter boxes (surely_below): float64 boxes and thr >= 1e-2 only, else plain disjointness
+  const double t_shrink = (sizeof(T) == 8 && a.thr >= 1e-2 && a.thr < 1e30) ? fmin(a.thr, 1.0) * 0.999999 : 0.0;
+
   // ---- 3. gather sorted boxes ----
   BoxC<T>* sb = reinterpret_cast<BoxC<T>*>(a.sorted_boxes) + base;
   float4* sf4 = a.sorted_f4 + base;
+  float4* sf4s = a.sorted_f4s + base;
   float4* sf4i = a.sorted_f4i + base;
   float2* sarea = a.sorted_area + base;
   int* scls = a.sorted_cls + base;
@@ -508,19 +566,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     const BoxF bf = make_boxf((double)b.x1, (double)b.y1, (double)b.x2, (double)b.y2, (double)b.area);
     sf4[i] = bf.out; sf4i[i] = bf.in; sarea[i] = bf.area;
     scls[i] = a.cls ? a.cls[base + r] : 0;
-    flags[i] = box_finite(b) ? 0 : 4;
+    bool exact_only = !box_finite(b);
+    float4 shr = bf.out;
+    if (t_shrink > 0.0 && !exact_only) {
+      exact_only = !box_regular((double)b.x1, (double)b.y1, (double)b.x2, (double)b.y2, (double)b.area);
+      shr = shrunk_f4((double)b.x1, (double)b.y1, (double)b.x2, (double)b.y2, t_shrink);
+    }
+    sf4s[i] = shr;
+    flags[i] = exact_only ? 4 : 0;
     order[i] = r;          // provisional: sorted row ids; compacted to kept rows in step 5
   }
   __syncthreads();
 
   // ---- 4. blocked greedy sweep ----
-  const T thr = (T)a.thr;
-  const bool per_class = a.per_class != 0;
-  // iou == 0 never suppresses when thr > 0 (>=) / thr >= 0 (>): then surely disjoint pairs are skipped outright
-  const bool skip_disjoint = per_class ? (thr >= (T)0) : (thr > (T)0);
-  // float interval fast path (float64 boxes, positive threshold): bounds of thr (1 -+ 1e-6) rounded outwards
-  const bool use_f32 = sizeof(T) == 8 && a.thr > 1e-30 && a.thr < 1e30;
-  const float thr_dn = __double2float_rd(a.thr * 0.999999), thr_up = __double2float_ru(a.thr * 1.000001);
   for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
     const int nb = min(NMS_BLOCK, K - b0);
     if (tid < NMS_BLOCK) {
@@ -575,6 +633,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       s_kcls[pos] = s_cls[tid];
       s_knf[pos] = s_nf[tid];
       s_kf4[pos] = s_nf[tid] ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY) : s_f4[tid];
+      s_kf4s[pos] = s_nf[tid] ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY) : sf4s[b0 + tid];
       s_kf4i[pos] = sf4i[b0 + tid];
       s_karea[pos] = sarea[b0 + tid];
     }
@@ -597,19 +656,20 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         unsigned long long todo = 0ull;
         bool sup = false;
         if (live && !(fj & 4)) {
-          oj = sf4[j]; ij = sf4i[j]; aj = sarea[j];
+          oj = sf4[j];
           unsigned lo = 0xffffffffu, hi = 0xffffffffu;
           if (skip_disjoint) {
+            const float4 sj = sf4s[j];
             lo = hi = 0u;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float4 fa = s_kf4[q], fb = s_kf4[q + 32];      // entries >= nkept are stale but masked off below
-              lo |= surely_disjoint(fa, oj) ? 0u : (1u << q);
-              hi |= surely_disjoint(fb, oj) ? 0u : (1u << q);
+            for (int q = 0; q < 32; ++q) {                         // entries >= nkept are stale but masked off below
+              or_unless_below(lo, 1u << q, s_kf4[q], s_kf4s[q], oj, sj);
+              or_unless_below(hi, 1u << q, s_kf4[q + 32], s_kf4s[q + 32], oj, sj);
             }
           }
           todo = ((unsigned long long)hi << 32) | lo;
           if (nkept < 64) todo &= (1ull << nkept) - 1ull;
+          if (todo) { ij = sf4i[j]; aj = sarea[j]; }
         } else if (live) {
           // a non-finite box j (rare): exact numpy-semantics IoU against every kept box, on this lane alone
           const BoxC<T> bj = sb[j];

@@ -238,3 +238,50 @@ def test_no_candidates_and_single_candidate():
     assert post.last_candidates[2] == int((head[2, :, 4] >= 0).sum()) and 0 < len(kept[2]) <= post.last_candidates[2]
     # a threshold nothing can reach empties the whole batch
     assert all(len(k) == 0 for k in post.run(head, 1.5, 0.6))
+
+
+def _clustered_boxes(rs, k, irregular):
+    """Jittered copies of a few base boxes (IoU values all over (0, 1), many near any threshold) with log-normal sizes;
+    optionally mixed with boxes the shrunk-corner prefilter must hand to the exact path: zero / negative extents,
+    extents vanishing against the coordinates, huge boxes."""
+    nb = max(1, k // 40)
+    bx, by = rs.uniform(0, 1, nb), rs.uniform(0, 1, nb)
+    bw, bh = 0.05 * np.exp(rs.normal(0, 1, nb)), 0.05 * np.exp(rs.normal(0, 1, nb))
+    pick = rs.randint(nb, size=k)
+    jit = rs.choice([0.02, 0.1, 0.4], size=k)
+    x = (bx[pick] + bw[pick] * jit * rs.normal(0, 1, k)).astype(np.float32)
+    y = (by[pick] + bh[pick] * jit * rs.normal(0, 1, k)).astype(np.float32)
+    w = bw[pick] * np.exp(jit * rs.normal(0, 1, k))
+    h = bh[pick] * np.exp(jit * rs.normal(0, 1, k))
+    if irregular:
+        idx = rs.permutation(k)
+        n = max(1, k // 25)
+        w[idx[:n]] = 0.0
+        h[idx[n:2 * n]] = -h[idx[n:2 * n]]
+        w[idx[2 * n:3 * n]] = -w[idx[2 * n:3 * n]]; h[idx[2 * n:3 * n]] = -h[idx[2 * n:3 * n]]
+        x[idx[3 * n:4 * n]] += np.float32(4096.0); w[idx[3 * n:4 * n]] = 1e-3      # W / |x| < 1e-4
+        w[idx[4 * n:5 * n]] = 1e6; h[idx[4 * n:5 * n]] = 1e6
+        w[idx[5 * n:6 * n]] = 1e-200; h[idx[5 * n:6 * n]] = 1e-200                # area underflows to 0
+    return {"x": x, "y": y, "w": w, "h": h, "prob": rs.uniform(.01, 1, k).astype(np.float32)}
+
+
+@pytest.mark.parametrize("k,seed,irregular", [(700, 0, False), (700, 1, True), (3000, 2, False), (3000, 3, True)])
+def test_nms_near_threshold_clusters_and_irregular_boxes(k, seed, irregular):
+    """The prefilter (float corners shrunk by thr * extent) may only drop pairs the exact float64 rule rejects:
+    kept lists stay bit-identical for thresholds below / at / above its switch-on point (1e-2) and beyond 1."""
+    c = _clustered_boxes(np.random.RandomState(100 + seed), k, irregular)
+    for thr in (0.003, 0.01, 0.0101, 0.3, 0.6, 0.9, 1.0, 1.25):
+        got = engine.nms(c["x"], c["y"], c["w"], c["h"], c["prob"], thr)
+        assert np.array_equal(got, postprocess.nms(c, thr)), thr
+
+
+def test_nms_dense_config5_image_vs_oracle():
+    """One image of BASELINE config 5 (10,647 candidates, N(0,1) logits, thresholds 0.001 / 0.6)."""
+    shape = (416, 416, 3)
+    post = _post_v3(shape, 1)
+    head = np.random.RandomState(0).standard_normal((1, 10647, 85)).astype(np.float32)
+    kept = post.run(head, 0.001, 0.6)
+    cand = post.decode(head, 0.001)
+    c = helpers.cand_from_dets(cand[0])
+    assert len(c["row"]) == 10647
+    assert np.array_equal(c["row"][postprocess.nms(c, 0.6)], kept[0]["row"])
