@@ -162,7 +162,7 @@ struct PostCtx {
   int* cls = nullptr;
   unsigned long long* keys = nullptr;
   void* sorted_boxes = nullptr;
-  float4 *sorted_f4 = nullptr, *sorted_f4s = nullptr, *sorted_f4i = nullptr;
+  float4 *sorted_f4 = nullptr, *sorted_f4s = nullptr, *sorted_f4i = nullptr, *sorted_ky = nullptr, *sorted_kx = nullptr;
   float2* sorted_area = nullptr;
   int* sorted_cls = nullptr;
   unsigned char* flags = nullptr;
@@ -183,6 +183,8 @@ struct PostCtx {
     YB_CUDA(cudaMalloc(&sorted_boxes, nr * sizeof(BoxC<double>)));
     YB_CUDA(cudaMalloc(&sorted_f4, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_f4s, nr * sizeof(float4)));
+    YB_CUDA(cudaMalloc(&sorted_ky, nr * sizeof(float4)));
+    YB_CUDA(cudaMalloc(&sorted_kx, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_f4i, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_area, nr * sizeof(float2)));
     YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
@@ -194,7 +196,7 @@ struct PostCtx {
   }
   void release() {
     cudaFree(prob); cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(h); cudaFree(cls); cudaFree(keys);
-    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4s); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
+    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4s); cudaFree(sorted_ky); cudaFree(sorted_kx); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
     cudaFree(dets);
     for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
   }
@@ -219,7 +221,7 @@ struct PostCtx {
   template <typename T, bool XY64, bool WH64>
   int nms_launch(cudaStream_t st, int n, const NmsArgs& a) {
     auto kern = sort_nms_kernel<T, XY64, WH64>;
-    const int smem = NMS_SMEM_KEYS * 8;
+    const int smem = NMS_DYN_SMEM;
     YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<n, NMS_THREADS, smem, st>>>(a);
     YB_CUDA(cudaGetLastError());
@@ -231,7 +233,7 @@ struct PostCtx {
     memset(&a, 0, sizeof(a));
     a.rows = rows; a.per_class = per_class; a.thr = thr;
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
+    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_ky = sorted_ky; a.sorted_kx = sorted_kx; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
     a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;
     return a;
   }

@@ -399,25 +399,6 @@ __device__ __forceinline__ bool surely_below(const float4& qo, const float4& qs,
   return (qs.z <= po.x) | (po.z <= qs.x) | (qs.w <= po.y) | (po.w <= qs.y) |
          (qo.z <= ps.x) | (ps.z <= qo.x) | (qo.w <= ps.y) | (ps.w <= qo.y);
 }
-// mask |= bit unless surely_below(...): one chained-predicate compare per corner and one predicated OR (the C++ form
-// compiles to a compare plus a select per corner).  No operand is NaN (non-finite boxes never get here).
-__device__ __forceinline__ void or_unless_below(unsigned& mask, unsigned bit, const float4& qo, const float4& qs,
-                                                const float4& po, const float4& ps) {
-  asm("{\n\t.reg .pred p;\n\t"
-      "setp.gt.f32 p, %2, %3;\n\t"
-      "setp.gt.and.f32 p, %4, %5, p;\n\t"
-      "setp.gt.and.f32 p, %6, %7, p;\n\t"
-      "setp.gt.and.f32 p, %8, %9, p;\n\t"
-      "setp.gt.and.f32 p, %10, %11, p;\n\t"
-      "setp.gt.and.f32 p, %12, %13, p;\n\t"
-      "setp.gt.and.f32 p, %14, %15, p;\n\t"
-      "setp.gt.and.f32 p, %16, %17, p;\n\t"
-      "@p or.b32 %0, %0, %1;\n\t}"
-      : "+r"(mask)
-      : "r"(bit), "f"(qs.z), "f"(po.x), "f"(po.z), "f"(qs.x), "f"(qs.w), "f"(po.y), "f"(po.w), "f"(qs.y),
-        "f"(qo.z), "f"(ps.x), "f"(ps.z), "f"(qo.x), "f"(qo.w), "f"(ps.y), "f"(ps.w), "f"(qo.y));
-}
-
 struct NmsArgs {
   int rows;             // R: dense rows per image (stride of every per-row array)
   int per_class;        // 0: reference (class-agnostic, >=); 1: per class, strict >
@@ -435,6 +416,8 @@ struct NmsArgs {
   void* sorted_boxes;   // BoxC<T> [n * rows]
   float4* sorted_f4;    // [n * rows]: outward-rounded float corners of the sorted boxes (disjointness prefilter)
   float4* sorted_f4s;   // [n * rows]: shrunk float corners (see surely_below); == sorted_f4 when shrinking is off
+  float4* sorted_kx;    // [n * rows]: (o.x, o.z, s.x, s.z) } the values a later box looks up in the kept block's sorted
+  float4* sorted_ky;    // [n * rows]: (o.y, o.w, s.y, s.w) } key tables (KeptBlock), conditions 0-3 and 4-7
   float4* sorted_f4i;   // [n * rows]: inward-rounded float corners          } float interval arithmetic,
   float2* sorted_area;  // [n * rows]: area rounded down / up to float       } see decide_f32
   int* sorted_cls;      // [n * rows]
@@ -471,6 +454,67 @@ __device__ __forceinline__ void bitonic_sort_desc(KeyPtr keys, int n_pow2) {
   }
 }
 
+// Generic sweep: the kept boxes of one block of NMS_BLOCK sorted boxes, compacted.  A non-finite or irregular kept box
+// carries all-covering prefilter corners, so the prefilter never drops it.
+template <typename T>
+struct KeptBlock {
+  float4 f4[NMS_BLOCK];      // outward-rounded corners
+  float4 f4s[NMS_BLOCK];     // shrunk corners
+  BoxC<T> box[NMS_BLOCK];
+  int cls[NMS_BLOCK];
+  int nkept;
+  unsigned char nf[NMS_BLOCK];
+};
+
+// Pipelined sweep: one block of NMS_BLOCK sorted boxes (not compacted: a kept box is named by its index in the block).
+//
+// Prefilter tables.  surely_below(q, p) is the negation of eight conditions "key_c(q) > v_c(p)" / "key_c(q) < v_c(p)":
+//   c: 0 qs.z > po.x   1 qs.x < po.z   2 qo.z > ps.x   3 qo.x < ps.z   4 qs.w > po.y   5 qs.y < po.w   6 qo.w > ps.y   7 qo.y < ps.w
+// For every condition the block's keys are sorted (skey[c] ascending, sidx[c] = box of each position, +inf padding)
+// and, once the kept set is known, tmask[c][r] is the set of KEPT boxes that satisfy the condition when r keys lie below
+// the looked-up value (r = #{key <= v} for the ">" conditions, r = #{key < v} for the "<" ones).  A later box finds r by
+// binary search, seven steps, and the AND of its eight masks is exactly the set of kept boxes that surely_below does
+// not exclude: O(log) per (box, block) instead of 64 pair tests.  Everything but tmask / kept depends on the geometry
+// of the block alone and is prepared one block ahead, off the critical path.
+template <typename T>
+struct SweepBlock {
+  unsigned long long tmask[8][NMS_BLOCK + 1];
+  unsigned long long pairmask[NMS_BLOCK];   // bit j of [i]: i < j and box i suppresses box j
+  unsigned long long kept;
+  float skey[8][NMS_BLOCK];
+  float4 f4[NMS_BLOCK];      // outward-rounded corners   } all-covering for an exact-only box
+  float4 f4s[NMS_BLOCK];     // shrunk corners            }
+  float4 f4i[NMS_BLOCK];     // inward-rounded corners
+  BoxC<T> box[NMS_BLOCK];
+  float2 area[NMS_BLOCK];
+  int cls[NMS_BLOCK];
+  int nb;
+  unsigned char sidx[8][NMS_BLOCK];
+  unsigned char nf[NMS_BLOCK];
+};
+
+constexpr int NMS_RESOLVER_THREADS = 64;                       // warps 0-1 resolve the next block
+constexpr int NMS_Q2_ENTRIES = 64;                             // per warp: 32-bit (box, kept box) entries, decided 32 at a time
+constexpr int NMS_DYN_SMEM = NMS_SMEM_KEYS * 8;                // sort keys; afterwards the per-warp queues, sort scratch and
+                                                               // three SweepBlocks
+static_assert((NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4 + 8 * NMS_BLOCK * 8 + 3 * sizeof(SweepBlock<double>) <= NMS_DYN_SMEM, "NMS smem");
+__device__ __forceinline__ void nms_resolver_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NMS_RESOLVER_THREADS) : "memory"); }
+__device__ __forceinline__ float unorderable(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// r = #{k : sk[k] <= v} (INCL) or #{k : sk[k] < v} over the 64 ascending keys sk
+template <bool INCL>
+__device__ __forceinline__ int nms_rank(const float* sk, float v) {
+  int r = 0;
+#pragma unroll
+  for (int st = NMS_BLOCK / 2; st >= 1; st >>= 1) {
+    const float k = sk[r + st - 1];
+    r += (INCL ? (k <= v) : (k < v)) ? st : 0;
+  }
+  const float k = sk[r];
+  return r + ((INCL ? (k <= v) : (k < v)) ? 1 : 0);
+}
+
 template <typename T, bool XY64, bool WH64>
 __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs a) {
   extern __shared__ unsigned long long s_keys[];           // NMS_SMEM_KEYS
@@ -478,18 +522,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   __shared__ unsigned long long s_mask[NMS_BLOCK];
   __shared__ unsigned long long s_kept_mask;
   __shared__ unsigned s_alive[2];
-  __shared__ BoxC<T> s_kbox[NMS_BLOCK];        // the kept boxes of the current block, compacted
-  __shared__ float4 s_kf4[NMS_BLOCK];
-  __shared__ float4 s_kf4s[NMS_BLOCK];
-  __shared__ float4 s_kf4i[NMS_BLOCK];
-  __shared__ float2 s_karea[NMS_BLOCK];
-  __shared__ int s_kcls[NMS_BLOCK];
-  __shared__ unsigned char s_knf[NMS_BLOCK];
+  __shared__ KeptBlock<T> s_kb;                // generic sweep: the kept boxes of the current block
   __shared__ BoxC<T> s_box[NMS_BLOCK];
   __shared__ float4 s_f4[NMS_BLOCK];
+  __shared__ float4 s_f4s[NMS_BLOCK];
   __shared__ int s_cls[NMS_BLOCK];
   __shared__ unsigned char s_nf[NMS_BLOCK];
   __shared__ int s_scan[32];
+  __shared__ int s_next[2];                    // next group of 32 later boxes of the sweep (per kept-block buffer)
   __shared__ int s_running;
 
   const int img = blockIdx.x;
@@ -549,6 +589,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   BoxC<T>* sb = reinterpret_cast<BoxC<T>*>(a.sorted_boxes) + base;
   float4* sf4 = a.sorted_f4 + base;
   float4* sf4s = a.sorted_f4s + base;
+  float4* sky = a.sorted_ky + base;
+  float4* skx = a.sorted_kx + base;
   float4* sf4i = a.sorted_f4i + base;
   float2* sarea = a.sorted_area + base;
   int* scls = a.sorted_cls + base;
@@ -573,198 +615,405 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       shr = shrunk_f4((double)b.x1, (double)b.y1, (double)b.x2, (double)b.y2, t_shrink);
     }
     sf4s[i] = shr;
+    sky[i] = make_float4(bf.out.y, bf.out.w, shr.y, shr.w);
+    skx[i] = make_float4(bf.out.x, bf.out.z, shr.x, shr.z);
     flags[i] = exact_only ? 4 : 0;
     order[i] = r;          // provisional: sorted row ids; compacted to kept rows in step 5
   }
   __syncthreads();
 
   // ---- 4. blocked greedy sweep ----
-  for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
-    const int nb = min(NMS_BLOCK, K - b0);
-    if (tid < NMS_BLOCK) {
-      s_mask[tid] = 0ull;
-      if (tid < nb) { s_box[tid] = sb[b0 + tid]; s_f4[tid] = sf4[b0 + tid]; s_cls[tid] = scls[b0 + tid]; s_nf[tid] = flags[b0 + tid] & 4; }
-    }
-    __syncthreads();
-    // 4a. intra-block pair mask: bit j of s_mask[i] set iff i<j and box i suppresses box j
-    for (int pidx = tid; pidx < NMS_BLOCK * NMS_BLOCK; pidx += NMS_THREADS) {
-      const int i = pidx >> 6, j = pidx & 63;
-      if (i < j && j < nb) {
-        if (per_class && s_cls[i] != s_cls[j]) continue;
-        bool sup;
-        if (s_nf[i] | s_nf[j]) {
-          const T v = iou_ref<T, true>(s_box[i], s_box[j]);
+  // Blocks of NMS_BLOCK sorted boxes.  Resolving a block = (a) its 64 x 64 pair mask, (b) the sequential greedy pass over
+  // that mask by one thread, (c) a compacted copy of its kept boxes (KeptBlock).  Sweeping a block = every kept box of it
+  // suppresses all later boxes.  Equivalent to the reference's loop: a box is kept iff no previously KEPT box reaches
+  // iou >= thr with it.
+  const int warp = tid >> 5, lane = tid & 31;
+  const float4 all_covering = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
+
+  // resolve the block starting at c0 (threads 0..63 only): first apply the kept boxes of the previous block (prev, may
+  // be null) to its boxes, then (a)-(c) into out.
+  auto resolve_block = [&](const int c0, const KeptBlock<T>* prev, KeptBlock<T>& out) {
+    const int nb = min(NMS_BLOCK, K - c0);
+    const int i = c0 + tid;
+    const bool have = tid < nb;
+    unsigned char f = have ? flags[i] : (unsigned char)1;
+    BoxC<T> bx;
+    bx.x1 = bx.y1 = bx.x2 = bx.y2 = bx.area = (T)0;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f), sh = o;
+    int c = 0;
+    if (have) { bx = sb[i]; o = sf4[i]; sh = sf4s[i]; c = scls[i]; }
+    if (prev != nullptr && have && !(f & 1)) {
+      const int nk = prev->nkept;
+      bool sup = false;
+      for (int q = 0; q < nk && !sup; ++q) {
+        if (per_class && prev->cls[q] != c) continue;
+        if ((f & 4) | prev->nf[q]) {
+          const T v = iou_ref<T, true>(prev->box[q], bx);
           sup = per_class ? (v > thr) : (v >= thr);
         } else {
-          if (skip_disjoint && surely_disjoint(s_f4[i], s_f4[j])) continue;
-          sup = suppresses_finite<T>(s_box[i], s_box[j], thr, per_class);
+          if (skip_disjoint && surely_below(prev->f4[q], prev->f4s[q], o, sh)) continue;
+          sup = suppresses_finite<T>(prev->box[q], bx, thr, per_class);
         }
-        if (sup) atomicOr(&s_mask[i], 1ull << j);
       }
+      if (sup) { f |= 1; flags[i] = f; }
     }
-    __syncthreads();
-    // 4b. sequential resolution of the block by one thread (everything it touches is in shared memory / registers)
-    if (tid < 64) {
-      const bool alive_t = tid < nb && !(flags[b0 + tid] & 1);
-      const unsigned bal = __ballot_sync(0xffffffffu, alive_t);
-      if ((tid & 31) == 0) s_alive[tid >> 5] = bal;
+    s_box[tid] = bx; s_f4[tid] = o; s_f4s[tid] = sh; s_cls[tid] = c; s_nf[tid] = f & 4; s_mask[tid] = 0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, have && !(f & 1));
+    if (lane == 0) s_alive[warp] = bal;
+    nms_resolver_barrier();
+    // (a) pair mask: bit j of s_mask[i] set iff i < j and box i suppresses box j.  Rows u and 62 - u hold 64 pairs
+    // together, one per thread; row 31 is left to the upper half of the threads.
+    for (int u = 0; u < 32; ++u) {
+      int pi, pj;
+      if (tid > u) { pi = u; pj = tid; } else { pi = 62 - u; pj = 63 - tid; }
+      if ((u == 31 && tid <= u) || pj >= nb) continue;
+      if (per_class && s_cls[pi] != s_cls[pj]) continue;
+      bool sup;
+      if (s_nf[pi] | s_nf[pj]) {
+        const T v = iou_ref<T, true>(s_box[pi], s_box[pj]);
+        sup = per_class ? (v > thr) : (v >= thr);
+      } else {
+        if (skip_disjoint && surely_below(s_f4[pi], s_f4s[pi], s_f4[pj], s_f4s[pj])) continue;
+        sup = suppresses_finite<T>(s_box[pi], s_box[pj], thr, per_class);
+      }
+      if (sup) atomicOr(&s_mask[pi], 1ull << pj);
     }
-    __syncthreads();
+    nms_resolver_barrier();
+    // (b) sequential pass, branch-free, the masks fetched eight at a time ahead of the dependent chain
     if (tid == 0) {
       unsigned long long alive = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
       unsigned long long kept = 0ull;
-      for (int i = 0; i < nb; ++i) {
-        if (alive & (1ull << i)) {
-          kept |= (1ull << i);
-          alive &= ~s_mask[i];
+      for (int i0 = 0; i0 < NMS_BLOCK; i0 += 8) {
+        unsigned long long m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m[u] = s_mask[i0 + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned long long bit = (alive >> (i0 + u)) & 1ull;
+          kept |= bit << (i0 + u);
+          alive &= ~(m[u] & (0ull - bit));
         }
       }
       s_kept_mask = kept;
     }
-    __syncthreads();
+    nms_resolver_barrier();
+    // (c) compacted copy of the kept boxes
     const unsigned long long kept = s_kept_mask;
-    const int nkept = __popcll(kept);
-    if (tid < nb && (kept >> tid) & 1ull) {
-      flags[b0 + tid] |= 2;
-      // compact copy of the kept boxes of this block; a non-finite box gets an all-covering float box so the
-      // disjointness test never drops it
+    if (have && ((kept >> tid) & 1ull)) {
+      flags[i] = f | 2;
       const int pos = __popcll(kept & ((1ull << tid) - 1ull));
-      s_kbox[pos] = s_box[tid];
-      s_kcls[pos] = s_cls[tid];
-      s_knf[pos] = s_nf[tid];
-      s_kf4[pos] = s_nf[tid] ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY) : s_f4[tid];
-      s_kf4s[pos] = s_nf[tid] ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY) : sf4s[b0 + tid];
-      s_kf4i[pos] = sf4i[b0 + tid];
-      s_karea[pos] = sarea[b0 + tid];
+      const bool nf = (f & 4) != 0;
+      out.box[pos] = bx; out.cls[pos] = c; out.nf[pos] = nf ? 1 : 0;
+      out.f4[pos] = nf ? all_covering : o; out.f4s[pos] = nf ? all_covering : sh;
     }
-    __syncthreads();
-    // 4c. every kept box of this block suppresses all later boxes.  Per later box j: (1) the cheap float test against
-    // all kept boxes gives a 64-bit mask of those that may overlap j; (2) only those pairs get a decision.
-    if (nkept > 0 && use_f32) {
-      // Flattened variant (float64 boxes, the engine's regime): the (j, kept box) pairs of the warp's 32 boxes are
-      // written to a per-warp queue (in the shared memory the sort keys no longer need) and evaluated 32 at a time, so
-      // every lane works whatever the distribution of candidates over the lanes; the j box travels by shuffle.
-      unsigned short* wq = reinterpret_cast<unsigned short*>(s_keys) + (tid >> 5) * 2048;
-      const int lane = tid & 31;
-      for (int j0 = b0 + NMS_BLOCK + (tid & ~31); j0 < K; j0 += NMS_THREADS) {
-        const int j = j0 + lane;
-        const unsigned char fj = (j < K) ? flags[j] : (unsigned char)1;
-        const bool live = !(fj & 1);
-        const int cj = (per_class && live) ? scls[j] : 0;
-        float4 oj = make_float4(0.f, 0.f, 0.f, 0.f), ij = oj;
-        float2 aj = make_float2(0.f, 0.f);
-        unsigned long long todo = 0ull;
-        bool sup = false;
-        if (live && !(fj & 4)) {
-          oj = sf4[j];
-          unsigned lo = 0xffffffffu, hi = 0xffffffffu;
-          if (skip_disjoint) {
-            const float4 sj = sf4s[j];
-            lo = hi = 0u;
+    if (tid == 0) out.nkept = __popcll(kept);
+  };
+
+  if (use_f32) {
+    // Pipelined variant (float64 boxes, positive threshold: the engine's regime).  While all warps sweep the boxes after
+    // block b + 1 with the kept boxes of block b, warps 0-1 first FINALIZE block b + 1 (apply the kept boxes of block b
+    // to it, sequential greedy pass over its pair mask, prefilter tables of its kept set: the only steps that depend on
+    // block b) and then PREPARE block b + 2 (staging, pair mask, sorted keys: geometry only), so the sequential chain
+    // from block to block is short and hidden behind the sweep.  Groups of 32 later boxes are handed out through a shared
+    // counter.  A lane looks its box up in the eight key tables of the block (SweepBlock); the (box, kept box) pairs the
+    // prefilter cannot exclude go to a per-warp queue that is carried across groups and decided 32 entries at a time
+    // (float interval arithmetic, exact float64 when too close), so every lane works in both phases.
+    unsigned char* dyn = reinterpret_cast<unsigned char*>(s_keys);
+    unsigned* wq2 = reinterpret_cast<unsigned*>(dyn) + warp * NMS_Q2_ENTRIES;
+    unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(dyn + (NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4);
+    SweepBlock<T>* blks = reinterpret_cast<SweepBlock<T>*>(dyn + (NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4 + 8 * NMS_BLOCK * 8);
+
+    // the set of kept boxes of blk that surely_below does not exclude for the later box with lookup values vx, vy
+    auto candidates = [&](const SweepBlock<T>& blk, const float4& vx, const float4& vy) -> unsigned long long {
+      const int r0 = nms_rank<true>(blk.skey[0], vx.x), r1 = nms_rank<false>(blk.skey[1], vx.y);
+      const int r2 = nms_rank<true>(blk.skey[2], vx.z), r3 = nms_rank<false>(blk.skey[3], vx.w);
+      const int r4 = nms_rank<true>(blk.skey[4], vy.x), r5 = nms_rank<false>(blk.skey[5], vy.y);
+      const int r6 = nms_rank<true>(blk.skey[6], vy.z), r7 = nms_rank<false>(blk.skey[7], vy.w);
+      return blk.tmask[0][r0] & blk.tmask[1][r1] & blk.tmask[2][r2] & blk.tmask[3][r3] &
+             blk.tmask[4][r4] & blk.tmask[5][r5] & blk.tmask[6][r6] & blk.tmask[7][r7];
+    };
+    // exact-only later box bj (rare): numpy-semantics IoU against every kept box of blk
+    auto exact_scan = [&](const SweepBlock<T>& blk, const BoxC<T>& bj, const int cj) -> bool {
+      unsigned long long km = blk.kept;
+      bool sup = false;
+      while (km && !sup) {
+        const int q = __ffsll((long long)km) - 1;
+        km &= km - 1ull;
+        if (per_class && blk.cls[q] != cj) continue;
+        const T v = iou_ref<T, true>(blk.box[q], bj);
+        sup = per_class ? (v > thr) : (v >= thr);
+      }
+      return sup;
+    };
+
+    // PREPARE (threads 0..63): everything about the block at c0 that its geometry alone determines
+    auto prepare_block = [&](const int c0, SweepBlock<T>& blk) {
+      const int nb = min(NMS_BLOCK, K - c0);
+      const int i = c0 + tid;
+      const bool have = tid < nb;
+      BoxC<T> bx;
+      bx.x1 = bx.y1 = bx.x2 = bx.y2 = bx.area = (T)0;
+      float4 o = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), sh = o, fi = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 ar = make_float2(0.f, 0.f);
+      int c = 0;
+      bool nf = false;
+      if (have) {
+        bx = sb[i]; c = scls[i]; fi = sf4i[i]; ar = sarea[i];
+        nf = (flags[i] & 4) != 0;
+        o = nf ? all_covering : sf4[i];
+        sh = nf ? all_covering : sf4s[i];
+      }
+      blk.box[tid] = bx; blk.cls[tid] = c; blk.nf[tid] = nf ? 1 : 0; blk.f4[tid] = o; blk.f4s[tid] = sh; blk.f4i[tid] = fi;
+      blk.area[tid] = ar; blk.pairmask[tid] = 0ull;
+      if (tid == 0) blk.nb = nb;
+      {
+        // a padding entry (tid >= nb) sorts last (+inf) and never enters a mask
+        const float key[8] = {sh.z, have ? sh.x : INFINITY, o.z, have ? o.x : INFINITY, sh.w, have ? sh.y : INFINITY, o.w, have ? o.y : INFINITY};
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {                         // entries >= nkept are stale but masked off below
-              or_unless_below(lo, 1u << q, s_kf4[q], s_kf4s[q], oj, sj);
-              or_unless_below(hi, 1u << q, s_kf4[q + 32], s_kf4s[q + 32], oj, sj);
+        for (int cnd = 0; cnd < 8; ++cnd) s_sort[cnd * NMS_BLOCK + tid] = ((unsigned long long)orderable(key[cnd]) << 32) | (unsigned)tid;
+      }
+      nms_resolver_barrier();
+      // pair mask: rows u and 62 - u hold 64 pairs together, one per thread; row 31 is left to the upper half
+      for (int u = 0; u < 32; ++u) {
+        int pi, pj;
+        if (tid > u) { pi = u; pj = tid; } else { pi = 62 - u; pj = 63 - tid; }
+        if ((u == 31 && tid <= u) || pj >= nb) continue;
+        if (per_class && blk.cls[pi] != blk.cls[pj]) continue;
+        bool sup;
+        if (blk.nf[pi] | blk.nf[pj]) {
+          const T v = iou_ref<T, true>(blk.box[pi], blk.box[pj]);
+          sup = per_class ? (v > thr) : (v >= thr);
+        } else {
+          if (surely_below(blk.f4[pi], blk.f4s[pi], blk.f4[pj], blk.f4s[pj])) continue;
+          sup = suppresses_finite<T>(blk.box[pi], blk.box[pj], thr, per_class);
+        }
+        if (sup) atomicOr(&blk.pairmask[pi], 1ull << pj);
+      }
+      if (c0 + NMS_BLOCK >= K) return;          // the last block: nothing comes after it, no tables needed
+      // sorted keys: each of the two warps sorts four of the eight key arrays (bitonic, 64 keys, two per lane), the four
+      // independent sorts interleaved
+      unsigned long long* sk = s_sort + warp * 4 * NMS_BLOCK;
+      for (int k = 2; k <= NMS_BLOCK; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const int lo_i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1)), hi_i = lo_i | j;
+          const bool asc = (lo_i & k) == 0;
+          unsigned long long va[4], vb[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) { va[m] = sk[m * NMS_BLOCK + lo_i]; vb[m] = sk[m * NMS_BLOCK + hi_i]; }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if ((va[m] > vb[m]) == asc) { sk[m * NMS_BLOCK + lo_i] = vb[m]; sk[m * NMS_BLOCK + hi_i] = va[m]; }
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const unsigned long long e0 = sk[m * NMS_BLOCK + lane], e1 = sk[m * NMS_BLOCK + lane + 32];
+        blk.skey[warp * 4 + m][lane] = unorderable((uint32_t)(e0 >> 32));
+        blk.skey[warp * 4 + m][lane + 32] = unorderable((uint32_t)(e1 >> 32));
+        blk.sidx[warp * 4 + m][lane] = (unsigned char)(e0 & 63ull);
+        blk.sidx[warp * 4 + m][lane + 32] = (unsigned char)(e1 & 63ull);
+      }
+      __syncwarp();
+    };
+
+    // FINALIZE (threads 0..63): apply the kept boxes of prev (may be null) to the prepared block at c0, then its kept set
+    // and the tables of that set
+    auto finalize_block = [&](const int c0, SweepBlock<T>& blk, const SweepBlock<T>* prev) {
+      const int nb = min(NMS_BLOCK, K - c0);
+      const int i = c0 + tid;
+      const bool have = tid < nb;
+      unsigned char f = have ? flags[i] : (unsigned char)1;
+      if (prev != nullptr && have && !(f & 1) && prev->kept != 0ull) {
+        bool sup = false;
+        if (!(f & 4)) {
+          unsigned long long todo = candidates(*prev, skx[i], sky[i]);
+          while (todo && !sup) {
+            const int q = __ffsll((long long)todo) - 1;
+            todo &= todo - 1ull;
+            if (per_class && prev->cls[q] != blk.cls[tid]) continue;
+            if (prev->nf[q]) {
+              const T v = iou_ref<T, true>(prev->box[q], blk.box[tid]);
+              sup = per_class ? (v > thr) : (v >= thr);
+            } else {
+              sup = suppresses_finite<T>(prev->box[q], blk.box[tid], thr, per_class);
             }
           }
-          todo = ((unsigned long long)hi << 32) | lo;
-          if (nkept < 64) todo &= (1ull << nkept) - 1ull;
-          if (todo) { ij = sf4i[j]; aj = sarea[j]; }
-        } else if (live) {
-          // a non-finite box j (rare): exact numpy-semantics IoU against every kept box, on this lane alone
-          const BoxC<T> bj = sb[j];
-          for (int q = 0; q < nkept && !sup; ++q) {
-            if (per_class && s_kcls[q] != cj) continue;
-            const T v = iou_ref<T, true>(s_kbox[q], bj);
-            sup = per_class ? (v > thr) : (v >= thr);
+        } else {
+          sup = exact_scan(*prev, blk.box[tid], blk.cls[tid]);
+        }
+        if (sup) { f |= 1; flags[i] = f; }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, have && !(f & 1));
+      if (lane == 0) s_alive[warp] = bal;
+      nms_resolver_barrier();
+      // sequential pass, branch-free, the masks fetched eight at a time ahead of the dependent chain
+      if (tid == 0) {
+        unsigned long long alive = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
+        unsigned long long kept = 0ull;
+        for (int i0 = 0; i0 < NMS_BLOCK; i0 += 8) {
+          unsigned long long m[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) m[u] = blk.pairmask[i0 + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const unsigned long long bit = (alive >> (i0 + u)) & 1ull;
+            kept |= bit << (i0 + u);
+            alive &= ~(m[u] & (0ull - bit));
           }
         }
-        // exclusive scan of the candidate counts over the warp
-        const int cnt = __popcll(todo);
-        int incl = cnt;
+        blk.kept = kept;
+      }
+      nms_resolver_barrier();
+      const unsigned long long kept = blk.kept;
+      if (have && ((kept >> tid) & 1ull)) flags[i] = f | 2;
+      if (c0 + NMS_BLOCK >= K) return;            // the last block
+      // tables of the kept set: suffix OR of the kept bits along each sorted order (warp w: conditions 4w .. 4w + 3)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int cnd = warp * 4 + m;
+        const int i0 = blk.sidx[cnd][lane], i1 = blk.sidx[cnd][lane + 32];
+        unsigned long long s0 = kept & (1ull << i0), s1 = kept & (1ull << i1);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += t;
+          const unsigned long long t0 = __shfl_down_sync(0xffffffffu, s0, d), t1 = __shfl_down_sync(0xffffffffu, s1, d);
+          if (lane + d < 32) { s0 |= t0; s1 |= t1; }
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int pos = incl - cnt;
-        while (todo) {
-          const int q = __ffsll((long long)todo) - 1;
-          todo &= todo - 1;
-          wq[pos++] = (unsigned short)((lane << 6) | q);
-        }
-        __syncwarp();
-        unsigned supmask = 0u;
-        for (int s0 = 0; s0 < total; s0 += 32) {
-          const bool valid = s0 + lane < total;
-          const unsigned e = valid ? wq[s0 + lane] : 0u;
-          const int l = (int)(e >> 6), q = (int)(e & 63u);
-          float4 o2, i2;
-          float2 a2;
-          o2.x = __shfl_sync(0xffffffffu, oj.x, l); o2.y = __shfl_sync(0xffffffffu, oj.y, l);
-          o2.z = __shfl_sync(0xffffffffu, oj.z, l); o2.w = __shfl_sync(0xffffffffu, oj.w, l);
-          i2.x = __shfl_sync(0xffffffffu, ij.x, l); i2.y = __shfl_sync(0xffffffffu, ij.y, l);
-          i2.z = __shfl_sync(0xffffffffu, ij.z, l); i2.w = __shfl_sync(0xffffffffu, ij.w, l);
-          a2.x = __shfl_sync(0xffffffffu, aj.x, l); a2.y = __shfl_sync(0xffffffffu, aj.y, l);
-          const int c2 = per_class ? __shfl_sync(0xffffffffu, cj, l) : 0;
-          bool hit = false;
-          if (valid && !(per_class && s_kcls[q] != c2)) {
-            const int d = s_knf[q] ? 0 : decide_f32(s_kf4[q], s_kf4i[q], s_karea[q], o2, i2, a2, thr_dn, thr_up);
-            hit = d > 0;
-            if (d == 0) {                       // too close to the threshold (or a non-finite kept box): exact float64
-              const BoxC<T> bl = sb[j0 + l];
-              if (s_knf[q]) {
-                const T v = iou_ref<T, true>(s_kbox[q], bl);
-                hit = per_class ? (v > thr) : (v >= thr);
-              } else {
-                hit = suppresses_finite<T>(s_kbox[q], bl, thr, per_class);
+        s0 |= __shfl_sync(0xffffffffu, s1, 0);
+        // ">" conditions (even): positions >= r satisfy; "<" conditions (odd): positions < r satisfy
+        const bool less = (cnd & 1) != 0;
+        blk.tmask[cnd][lane] = less ? (kept & ~s0) : s0;
+        blk.tmask[cnd][lane + 32] = less ? (kept & ~s1) : s1;
+        if (lane == 0) blk.tmask[cnd][NMS_BLOCK] = less ? kept : 0ull;
+      }
+    };
+
+    if (tid < NMS_RESOLVER_THREADS) {
+      prepare_block(0, blks[0]);
+      nms_resolver_barrier();
+      finalize_block(0, blks[0], nullptr);
+      if (NMS_BLOCK < K) prepare_block(NMS_BLOCK, blks[1]);
+    }
+    if (tid == 0) { s_next[0] = 0; s_next[1] = 0; }
+    __syncthreads();
+    int bi = 0;                                   // block index modulo 3
+    for (int b0 = 0, par = 0; b0 < K; b0 += NMS_BLOCK, par ^= 1, bi = (bi == 2) ? 0 : bi + 1) {
+      const SweepBlock<T>& kc = blks[bi];
+      if (tid < NMS_RESOLVER_THREADS) {
+        const int b1 = (bi == 2) ? 0 : bi + 1, b2 = (b1 == 2) ? 0 : b1 + 1;
+        if (b0 + NMS_BLOCK < K) finalize_block(b0 + NMS_BLOCK, blks[b1], &kc);
+        if (b0 + 2 * NMS_BLOCK < K) prepare_block(b0 + 2 * NMS_BLOCK, blks[b2]);
+        if (tid == 0) s_next[par ^ 1] = 0;
+      }
+      if (kc.kept != 0ull) {
+        int n2 = 0;                              // entries in the queue (warp-uniform)
+        auto decide_entries = [&](const int n) {
+          if (lane < n) {
+            const unsigned e = wq2[lane];
+            const int jj = (int)(e >> 6), q = (int)(e & 63u);
+            const unsigned char fjj = flags[jj];
+            if (!(fjj & 1) && !(per_class && kc.cls[q] != scls[jj])) {
+              bool hit;
+              int d = 0;
+              if (!kc.nf[q]) d = decide_f32(kc.f4[q], kc.f4i[q], kc.area[q], sf4[jj], sf4i[jj], sarea[jj], thr_dn, thr_up);
+              hit = d > 0;
+              if (d == 0) {                     // too close to the threshold (or an exact-only kept box): float64
+                const BoxC<T> bl = sb[jj];
+                if (kc.nf[q]) {
+                  const T v = iou_ref<T, true>(kc.box[q], bl);
+                  hit = per_class ? (v > thr) : (v >= thr);
+                } else {
+                  hit = suppresses_finite<T>(kc.box[q], bl, thr, per_class);
+                }
               }
+              if (hit) flags[jj] = fjj | 1;     // several lanes may store the same byte: same value
             }
           }
-          supmask |= __reduce_or_sync(0xffffffffu, hit ? (1u << l) : 0u);
-        }
-        if (live && (sup || ((supmask >> lane) & 1u))) flags[j] = fj | 1;
-        __syncwarp();                           // the queue is rewritten by the next group of 32 boxes
-      }
-    } else if (nkept > 0) {
-      for (int j = b0 + NMS_BLOCK + tid; j < K; j += NMS_THREADS) {
-        const unsigned char fj = flags[j];
-        if (fj & 1) continue;
-        const int cj = per_class ? scls[j] : 0;
-        unsigned lo = 0xffffffffu, hi = 0xffffffffu;
-        if (skip_disjoint && !(fj & 4)) {
-          const float4 f4j = sf4[j];
-          lo = hi = 0u;
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float4 fa = s_kf4[q], fb = s_kf4[q + 32];      // entries >= nkept are stale but masked off below
-            lo |= surely_disjoint(fa, f4j) ? 0u : (1u << q);
-            hi |= surely_disjoint(fb, f4j) ? 0u : (1u << q);
+        };
+        const int first = b0 + 2 * NMS_BLOCK;
+        while (true) {
+          int g = 0;
+          if (lane == 0) g = atomicAdd(&s_next[par], 1);
+          g = __shfl_sync(0xffffffffu, g, 0);
+          const int j0 = first + g * 32;
+          if (j0 >= K) break;
+          const int j = j0 + lane;
+          const unsigned char fj = (j < K) ? flags[j] : (unsigned char)1;
+          const bool live = !(fj & 1);
+          unsigned long long todo = 0ull;
+          if (live && !(fj & 4)) {
+            todo = candidates(kc, skx[j], sky[j]);
+          } else if (live) {
+            if (exact_scan(kc, sb[j], per_class ? scls[j] : 0)) flags[j] = fj | 1;
+          }
+          // surviving pairs -> queue, one per lane and round
+          while (__any_sync(0xffffffffu, todo != 0ull)) {
+            const bool has = todo != 0ull;
+            const int q = has ? __ffsll((long long)todo) - 1 : 0;
+            todo &= todo - 1ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (has) wq2[n2 + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)j << 6) | (unsigned)q;
+            n2 += __popc(bal);
+            __syncwarp();
+            if (n2 >= 32) {
+              decide_entries(32);
+              const unsigned rest = (32 + lane < n2) ? wq2[32 + lane] : 0u;
+              __syncwarp();
+              if (32 + lane < n2) wq2[lane] = rest;
+              n2 -= 32;
+              __syncwarp();
+            }
           }
         }
-        unsigned long long todo = ((unsigned long long)hi << 32) | lo;
-        if (nkept < 64) todo &= (1ull << nkept) - 1ull;
-        if (todo == 0ull) continue;
-        bool sup = false;
-        if (todo) {
+        decide_entries(n2);
+      }
+      __syncthreads();
+    }
+  } else {
+    // Generic variant (float32 boxes, or a threshold that every pair has to be evaluated for): block after block.
+    for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
+      if (tid < NMS_RESOLVER_THREADS) resolve_block(b0, nullptr, s_kb);
+      __syncthreads();
+      const KeptBlock<T>& kc = s_kb;
+      const int nkept = kc.nkept;
+      if (nkept > 0) {
+        for (int j = b0 + NMS_BLOCK + tid; j < K; j += NMS_THREADS) {
+          const unsigned char fj = flags[j];
+          if (fj & 1) continue;
+          const int cj = per_class ? scls[j] : 0;
+          unsigned lo = 0xffffffffu, hi = 0xffffffffu;
+          if (skip_disjoint && !(fj & 4)) {
+            const float4 f4j = sf4[j];
+            lo = hi = 0u;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float4 fa = kc.f4[q], fb = kc.f4[q + 32];      // entries >= nkept are stale but masked off below
+              lo |= surely_disjoint(fa, f4j) ? 0u : (1u << q);
+              hi |= surely_disjoint(fb, f4j) ? 0u : (1u << q);
+            }
+          }
+          unsigned long long todo = ((unsigned long long)hi << 32) | lo;
+          if (nkept < 64) todo &= (1ull << nkept) - 1ull;
+          if (todo == 0ull) continue;
+          bool sup = false;
           const BoxC<T> bj = sb[j];
           while (todo && !sup) {
             const int q = __ffsll((long long)todo) - 1;
             todo &= todo - 1;
-            if (per_class && s_kcls[q] != cj) continue;
-            if ((fj & 4) | s_knf[q]) {
-              const T v = iou_ref<T, true>(s_kbox[q], bj);
+            if (per_class && kc.cls[q] != cj) continue;
+            if ((fj & 4) | kc.nf[q]) {
+              const T v = iou_ref<T, true>(kc.box[q], bj);
               sup = per_class ? (v > thr) : (v >= thr);
             } else {
-              sup = suppresses_finite<T>(s_kbox[q], bj, thr, per_class);
+              sup = suppresses_finite<T>(kc.box[q], bj, thr, per_class);
             }
           }
+          if (sup) flags[j] = fj | 1;
         }
-        if (sup) flags[j] = fj | 1;
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // ---- 5. ordered compaction of kept rows ----
