@@ -232,6 +232,7 @@ struct PostCtx {
     NmsArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = rows; a.per_class = per_class; a.thr = thr;
+    { const char* dbg = getenv("YB_NMS_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
     a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_ky = sorted_ky; a.sorted_kx = sorted_kx; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
     a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;

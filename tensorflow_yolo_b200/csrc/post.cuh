@@ -402,6 +402,7 @@ __device__ __forceinline__ bool surely_below(const float4& qo, const float4& qs,
 struct NmsArgs {
   int rows;             // R: dense rows per image (stride of every per-row array)
   int per_class;        // 0: reference (class-agnostic, >=); 1: per class, strict >
+  int debug;            // measurement only (YB_NMS_DEBUG): bit 0 skips the sweep of the pipelined variant (wrong results)
   double thr;
   // dense inputs [n * rows]; a NaN prob marks a non-candidate
   const float* prob;
@@ -431,6 +432,7 @@ struct NmsArgs {
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_SMEM_KEYS = 16384;   // 128 KB of 64-bit keys
 constexpr int NMS_BLOCK = 64;
+constexpr int NMS_QB = 128;            // buckets per condition of the direct-address prefilter tables
 
 __device__ __forceinline__ uint32_t orderable(float f) {
   const uint32_t b = __float_as_uint(f);
@@ -470,35 +472,46 @@ struct KeptBlock {
 //
 // Prefilter tables.  surely_below(q, p) is the negation of eight conditions "key_c(q) > v_c(p)" / "key_c(q) < v_c(p)":
 //   c: 0 qs.z > po.x   1 qs.x < po.z   2 qo.z > ps.x   3 qo.x < ps.z   4 qs.w > po.y   5 qs.y < po.w   6 qo.w > ps.y   7 qo.y < ps.w
-// For every condition the block's keys are sorted (skey[c] ascending, sidx[c] = box of each position, +inf padding)
-// and, once the kept set is known, tmask[c][r] is the set of KEPT boxes that satisfy the condition when r keys lie below
-// the looked-up value (r = #{key <= v} for the ">" conditions, r = #{key < v} for the "<" ones).  A later box finds r by
-// binary search, seven steps, and the AND of its eight masks is exactly the set of kept boxes that surely_below does
-// not exclude: O(log) per (box, block) instead of 64 pair tests.  Everything but tmask / kept depends on the geometry
-// of the block alone and is prepared one block ahead, off the critical path.
+// For every condition the block's keys are sorted (skey[c] ascending, +inf padding) and tmask[c][r] is the set of boxes
+// of the block that satisfy the condition when r keys lie below the looked-up value (r = #{key <= v} for the ">"
+// conditions, r = #{key < v} for the "<" ones).  A later box finds r by binary search, seven steps, and the AND of its
+// eight masks and the kept set is exactly the set of kept boxes that surely_below does not exclude: O(log) per
+// (box, block) instead of 64 pair tests.  The same lookup yields the block's own pair mask.  Everything but `kept`
+// depends on the geometry of the block alone and is prepared two blocks ahead, off the critical path.
+//
+// The sweep itself uses a direct-address form of the same tables: per condition the finite keys span [qlo, qhi], cut
+// into NMS_QB uniform buckets; qmask[c][b] is the table mask that holds for EVERY value of bucket b (the mask at the
+// bucket's lower edge for ">", at its upper edge for "<", edges widened by 1e-3 of a bucket against the float rounding of
+// the bucket index; the first / last bucket also take everything outside the span).  One multiply, one conversion and
+// one load per condition; the price is a prefilter that is up to one bucket looser per condition.
 template <typename T>
 struct SweepBlock {
+  unsigned long long qmask[8][NMS_QB];
+  float4 qlo[2], qscale[2];                 // per condition: bucket index = floor((v - qlo) * qscale), clamped
   unsigned long long tmask[8][NMS_BLOCK + 1];
   unsigned long long pairmask[NMS_BLOCK];   // bit j of [i]: i < j and box i suppresses box j
-  unsigned long long kept;
+  unsigned long long kept;                  // the only field that depends on the earlier blocks
   float skey[8][NMS_BLOCK];
   float4 f4[NMS_BLOCK];      // outward-rounded corners   } all-covering for an exact-only box
   float4 f4s[NMS_BLOCK];     // shrunk corners            }
   float4 f4i[NMS_BLOCK];     // inward-rounded corners
+  float4 vx[NMS_BLOCK];      // the boxes' own lookup values (sorted_kx / sorted_ky), for the block's turn as later boxes
+  float4 vy[NMS_BLOCK];
   BoxC<T> box[NMS_BLOCK];
   float2 area[NMS_BLOCK];
   int cls[NMS_BLOCK];
   int nb;
-  unsigned char sidx[8][NMS_BLOCK];
   unsigned char nf[NMS_BLOCK];
 };
 
-constexpr int NMS_RESOLVER_THREADS = 64;                       // warps 0-1 resolve the next block
+constexpr int NMS_RESOLVER_THREADS = 64;                       // warps 0-1 finalize the next block, warps 2-5 prepare the one after
 constexpr int NMS_Q2_ENTRIES = 64;                             // per warp: 32-bit (box, kept box) entries, decided 32 at a time
 constexpr int NMS_DYN_SMEM = NMS_SMEM_KEYS * 8;                // sort keys; afterwards the per-warp queues, sort scratch and
                                                                // three SweepBlocks
 static_assert((NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4 + 8 * NMS_BLOCK * 8 + 3 * sizeof(SweepBlock<double>) <= NMS_DYN_SMEM, "NMS smem");
 __device__ __forceinline__ void nms_resolver_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NMS_RESOLVER_THREADS) : "memory"); }
+constexpr int NMS_PREPARER_THREADS = 128;                      // warps 2-5
+__device__ __forceinline__ void nms_preparer_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(NMS_PREPARER_THREADS) : "memory"); }
 __device__ __forceinline__ float unorderable(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
@@ -711,19 +724,23 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
 
   if (use_f32) {
     // Pipelined variant (float64 boxes, positive threshold: the engine's regime).  While all warps sweep the boxes after
-    // block b + 1 with the kept boxes of block b, warps 0-1 first FINALIZE block b + 1 (apply the kept boxes of block b
-    // to it, sequential greedy pass over its pair mask, prefilter tables of its kept set: the only steps that depend on
-    // block b) and then PREPARE block b + 2 (staging, pair mask, sorted keys: geometry only), so the sequential chain
-    // from block to block is short and hidden behind the sweep.  Groups of 32 later boxes are handed out through a shared
-    // counter.  A lane looks its box up in the eight key tables of the block (SweepBlock); the (box, kept box) pairs the
-    // prefilter cannot exclude go to a per-warp queue that is carried across groups and decided 32 entries at a time
-    // (float interval arithmetic, exact float64 when too close), so every lane works in both phases.
+    // block b + 1 with the kept boxes of block b,
+    //   warps 0-1 FINALIZE block b + 1: apply the kept boxes of block b to it, then the sequential greedy pass over its
+    //             pair mask gives its kept set -- the only steps that depend on the earlier blocks;
+    //   warps 2-5 PREPARE block b + 2: staging, sorted keys, tables, pair mask -- geometry only;
+    // then both join the sweep, so the sequential chain from block to block is short and hidden.  Groups of 32 later
+    // boxes are handed out through a shared counter.  A lane looks its box up in the eight key tables of the block
+    // (SweepBlock); the (box, kept box) pairs the prefilter cannot exclude go to a per-warp queue that is carried across
+    // groups and decided 32 entries at a time (float interval arithmetic, exact float64 when too close), so every lane
+    // works in both phases.
     unsigned char* dyn = reinterpret_cast<unsigned char*>(s_keys);
     unsigned* wq2 = reinterpret_cast<unsigned*>(dyn) + warp * NMS_Q2_ENTRIES;
     unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(dyn + (NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4);
     SweepBlock<T>* blks = reinterpret_cast<SweepBlock<T>*>(dyn + (NMS_THREADS / 32) * NMS_Q2_ENTRIES * 4 + 8 * NMS_BLOCK * 8);
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define NMS_TICK(k) { if (a.debug & 2) { const long long now_ = clock64(); tm[k] += now_ - t_last; t_last = now_; } }
 
-    // the set of kept boxes of blk that surely_below does not exclude for the later box with lookup values vx, vy
+    // the boxes of blk that surely_below does not exclude for the later box with lookup values vx, vy
     auto candidates = [&](const SweepBlock<T>& blk, const float4& vx, const float4& vy) -> unsigned long long {
       const int r0 = nms_rank<true>(blk.skey[0], vx.x), r1 = nms_rank<false>(blk.skey[1], vx.y);
       const int r2 = nms_rank<true>(blk.skey[2], vx.z), r3 = nms_rank<false>(blk.skey[3], vx.w);
@@ -732,149 +749,85 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       return blk.tmask[0][r0] & blk.tmask[1][r1] & blk.tmask[2][r2] & blk.tmask[3][r3] &
              blk.tmask[4][r4] & blk.tmask[5][r5] & blk.tmask[6][r6] & blk.tmask[7][r7];
     };
-    // exact-only later box bj (rare): numpy-semantics IoU against every kept box of blk
-    auto exact_scan = [&](const SweepBlock<T>& blk, const BoxC<T>& bj, const int cj) -> bool {
-      unsigned long long km = blk.kept;
-      bool sup = false;
-      while (km && !sup) {
-        const int q = __ffsll((long long)km) - 1;
-        km &= km - 1ull;
-        if (per_class && blk.cls[q] != cj) continue;
+    // the direct-address form: a superset of candidates()
+    auto bucket_candidates = [&](const SweepBlock<T>& blk, const float4& vx, const float4& vy) -> unsigned long long {
+      const float4 la = blk.qlo[0], lb = blk.qlo[1], sa = blk.qscale[0], sb_ = blk.qscale[1];
+#define NMS_QIDX(v, l, sc) min(__float2uint_rd(__fmul_rn(__fsub_rn(v, l), sc)), (unsigned)(NMS_QB - 1))
+      const unsigned b0_ = NMS_QIDX(vx.x, la.x, sa.x), b1_ = NMS_QIDX(vx.y, la.y, sa.y), b2_ = NMS_QIDX(vx.z, la.z, sa.z), b3_ = NMS_QIDX(vx.w, la.w, sa.w);
+      const unsigned b4_ = NMS_QIDX(vy.x, lb.x, sb_.x), b5_ = NMS_QIDX(vy.y, lb.y, sb_.y), b6_ = NMS_QIDX(vy.z, lb.z, sb_.z), b7_ = NMS_QIDX(vy.w, lb.w, sb_.w);
+#undef NMS_QIDX
+      return blk.qmask[0][b0_] & blk.qmask[1][b1_] & blk.qmask[2][b2_] & blk.qmask[3][b3_] &
+             blk.qmask[4][b4_] & blk.qmask[5][b5_] & blk.qmask[6][b6_] & blk.qmask[7][b7_];
+    };
+    // the reference's decision for kept-role box q of blk against later-role box bj (either may be exact-only)
+    auto pair_suppresses = [&](const SweepBlock<T>& blk, const int q, const BoxC<T>& bj, const bool exact_j) -> bool {
+      if (exact_j | (blk.nf[q] != 0)) {
         const T v = iou_ref<T, true>(blk.box[q], bj);
-        sup = per_class ? (v > thr) : (v >= thr);
+        return per_class ? (v > thr) : (v >= thr);
       }
-      return sup;
+      return suppresses_finite<T>(blk.box[q], bj, thr, per_class);
     };
 
-    // PREPARE (threads 0..63): everything about the block at c0 that its geometry alone determines
+    // PREPARE (threads 64..191; box t = thread 64 + t): everything about the block at c0 that its geometry alone determines
     auto prepare_block = [&](const int c0, SweepBlock<T>& blk) {
+      const int t = tid - NMS_RESOLVER_THREADS, w = warp - NMS_RESOLVER_THREADS / 32;
       const int nb = min(NMS_BLOCK, K - c0);
-      const int i = c0 + tid;
-      const bool have = tid < nb;
+      const int i = c0 + t;
+      const bool have = t < nb;
+      long long t_last = clock64();
       BoxC<T> bx;
       bx.x1 = bx.y1 = bx.x2 = bx.y2 = bx.area = (T)0;
-      float4 o = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), sh = o, fi = make_float4(0.f, 0.f, 0.f, 0.f);
-      float2 ar = make_float2(0.f, 0.f);
+      float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
       int c = 0;
       bool nf = false;
-      if (have) {
-        bx = sb[i]; c = scls[i]; fi = sf4i[i]; ar = sarea[i];
-        nf = (flags[i] & 4) != 0;
-        o = nf ? all_covering : sf4[i];
-        sh = nf ? all_covering : sf4s[i];
-      }
-      blk.box[tid] = bx; blk.cls[tid] = c; blk.nf[tid] = nf ? 1 : 0; blk.f4[tid] = o; blk.f4s[tid] = sh; blk.f4i[tid] = fi;
-      blk.area[tid] = ar; blk.pairmask[tid] = 0ull;
-      if (tid == 0) blk.nb = nb;
-      {
-        // a padding entry (tid >= nb) sorts last (+inf) and never enters a mask
+      if (t < NMS_BLOCK) {
+        float4 o = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), sh = o, fi = vx;
+        float2 ar = make_float2(0.f, 0.f);
+        if (have) {
+          bx = sb[i]; c = scls[i]; fi = sf4i[i]; ar = sarea[i]; vx = skx[i]; vy = sky[i];
+          nf = (flags[i] & 4) != 0;
+          o = nf ? all_covering : sf4[i];
+          sh = nf ? all_covering : sf4s[i];
+        }
+        blk.box[t] = bx; blk.cls[t] = c; blk.nf[t] = nf ? 1 : 0; blk.f4[t] = o; blk.f4s[t] = sh; blk.f4i[t] = fi;
+        blk.area[t] = ar; blk.vx[t] = vx; blk.vy[t] = vy; blk.pairmask[t] = 0ull;
+        if (t == 0) blk.nb = nb;
+        // a padding entry (t >= nb) sorts last (+inf) and never enters a mask
         const float key[8] = {sh.z, have ? sh.x : INFINITY, o.z, have ? o.x : INFINITY, sh.w, have ? sh.y : INFINITY, o.w, have ? o.y : INFINITY};
 #pragma unroll
-        for (int cnd = 0; cnd < 8; ++cnd) s_sort[cnd * NMS_BLOCK + tid] = ((unsigned long long)orderable(key[cnd]) << 32) | (unsigned)tid;
+        for (int cnd = 0; cnd < 8; ++cnd) s_sort[cnd * NMS_BLOCK + t] = ((unsigned long long)orderable(key[cnd]) << 32) | (unsigned)t;
       }
-      nms_resolver_barrier();
-      // pair mask: rows u and 62 - u hold 64 pairs together, one per thread; row 31 is left to the upper half
-      for (int u = 0; u < 32; ++u) {
-        int pi, pj;
-        if (tid > u) { pi = u; pj = tid; } else { pi = 62 - u; pj = 63 - tid; }
-        if ((u == 31 && tid <= u) || pj >= nb) continue;
-        if (per_class && blk.cls[pi] != blk.cls[pj]) continue;
-        bool sup;
-        if (blk.nf[pi] | blk.nf[pj]) {
-          const T v = iou_ref<T, true>(blk.box[pi], blk.box[pj]);
-          sup = per_class ? (v > thr) : (v >= thr);
-        } else {
-          if (surely_below(blk.f4[pi], blk.f4s[pi], blk.f4[pj], blk.f4s[pj])) continue;
-          sup = suppresses_finite<T>(blk.box[pi], blk.box[pj], thr, per_class);
-        }
-        if (sup) atomicOr(&blk.pairmask[pi], 1ull << pj);
-      }
-      if (c0 + NMS_BLOCK >= K) return;          // the last block: nothing comes after it, no tables needed
-      // sorted keys: each of the two warps sorts four of the eight key arrays (bitonic, 64 keys, two per lane), the four
+      nms_preparer_barrier();
+      NMS_TICK(0)
+      // sorted keys: each of the four warps sorts two of the eight key arrays (bitonic, 64 keys, two per lane), the two
       // independent sorts interleaved
-      unsigned long long* sk = s_sort + warp * 4 * NMS_BLOCK;
+      unsigned long long* sk = s_sort + w * 2 * NMS_BLOCK;
       for (int k = 2; k <= NMS_BLOCK; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
           const int lo_i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1)), hi_i = lo_i | j;
           const bool asc = (lo_i & k) == 0;
-          unsigned long long va[4], vb[4];
+          unsigned long long va[2], vb[2];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) { va[m] = sk[m * NMS_BLOCK + lo_i]; vb[m] = sk[m * NMS_BLOCK + hi_i]; }
+          for (int m = 0; m < 2; ++m) { va[m] = sk[m * NMS_BLOCK + lo_i]; vb[m] = sk[m * NMS_BLOCK + hi_i]; }
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
+          for (int m = 0; m < 2; ++m) {
             if ((va[m] > vb[m]) == asc) { sk[m * NMS_BLOCK + lo_i] = vb[m]; sk[m * NMS_BLOCK + hi_i] = va[m]; }
           }
           __syncwarp();
         }
       }
+      NMS_TICK(1)
+      // tables: suffix OR of the boxes' bits along each sorted order; span of the finite keys (sorted: the -inf keys
+      // come first, the +inf keys and the padding last)
+      const unsigned long long all = nb < 64 ? (1ull << nb) - 1ull : ~0ull;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
+      for (int m = 0; m < 2; ++m) {
+        const int cnd = w * 2 + m;
         const unsigned long long e0 = sk[m * NMS_BLOCK + lane], e1 = sk[m * NMS_BLOCK + lane + 32];
-        blk.skey[warp * 4 + m][lane] = unorderable((uint32_t)(e0 >> 32));
-        blk.skey[warp * 4 + m][lane + 32] = unorderable((uint32_t)(e1 >> 32));
-        blk.sidx[warp * 4 + m][lane] = (unsigned char)(e0 & 63ull);
-        blk.sidx[warp * 4 + m][lane + 32] = (unsigned char)(e1 & 63ull);
-      }
-      __syncwarp();
-    };
-
-    // FINALIZE (threads 0..63): apply the kept boxes of prev (may be null) to the prepared block at c0, then its kept set
-    // and the tables of that set
-    auto finalize_block = [&](const int c0, SweepBlock<T>& blk, const SweepBlock<T>* prev) {
-      const int nb = min(NMS_BLOCK, K - c0);
-      const int i = c0 + tid;
-      const bool have = tid < nb;
-      unsigned char f = have ? flags[i] : (unsigned char)1;
-      if (prev != nullptr && have && !(f & 1) && prev->kept != 0ull) {
-        bool sup = false;
-        if (!(f & 4)) {
-          unsigned long long todo = candidates(*prev, skx[i], sky[i]);
-          while (todo && !sup) {
-            const int q = __ffsll((long long)todo) - 1;
-            todo &= todo - 1ull;
-            if (per_class && prev->cls[q] != blk.cls[tid]) continue;
-            if (prev->nf[q]) {
-              const T v = iou_ref<T, true>(prev->box[q], blk.box[tid]);
-              sup = per_class ? (v > thr) : (v >= thr);
-            } else {
-              sup = suppresses_finite<T>(prev->box[q], blk.box[tid], thr, per_class);
-            }
-          }
-        } else {
-          sup = exact_scan(*prev, blk.box[tid], blk.cls[tid]);
-        }
-        if (sup) { f |= 1; flags[i] = f; }
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, have && !(f & 1));
-      if (lane == 0) s_alive[warp] = bal;
-      nms_resolver_barrier();
-      // sequential pass, branch-free, the masks fetched eight at a time ahead of the dependent chain
-      if (tid == 0) {
-        unsigned long long alive = (unsigned long long)s_alive[0] | ((unsigned long long)s_alive[1] << 32);
-        unsigned long long kept = 0ull;
-        for (int i0 = 0; i0 < NMS_BLOCK; i0 += 8) {
-          unsigned long long m[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) m[u] = blk.pairmask[i0 + u];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const unsigned long long bit = (alive >> (i0 + u)) & 1ull;
-            kept |= bit << (i0 + u);
-            alive &= ~(m[u] & (0ull - bit));
-          }
-        }
-        blk.kept = kept;
-      }
-      nms_resolver_barrier();
-      const unsigned long long kept = blk.kept;
-      if (have && ((kept >> tid) & 1ull)) flags[i] = f | 2;
-      if (c0 + NMS_BLOCK >= K) return;            // the last block
-      // tables of the kept set: suffix OR of the kept bits along each sorted order (warp w: conditions 4w .. 4w + 3)
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int cnd = warp * 4 + m;
-        const int i0 = blk.sidx[cnd][lane], i1 = blk.sidx[cnd][lane + 32];
-        unsigned long long s0 = kept & (1ull << i0), s1 = kept & (1ull << i1);
+        const float k0 = unorderable((uint32_t)(e0 >> 32)), k1 = unorderable((uint32_t)(e1 >> 32));
+        blk.skey[cnd][lane] = k0;
+        blk.skey[cnd][lane + 32] = k1;
+        unsigned long long s0 = all & (1ull << (int)(e0 & 63ull)), s1 = all & (1ull << (int)(e1 & 63ull));
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const unsigned long long t0 = __shfl_down_sync(0xffffffffu, s0, d), t1 = __shfl_down_sync(0xffffffffu, s1, d);
@@ -883,30 +836,131 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         s0 |= __shfl_sync(0xffffffffu, s1, 0);
         // ">" conditions (even): positions >= r satisfy; "<" conditions (odd): positions < r satisfy
         const bool less = (cnd & 1) != 0;
-        blk.tmask[cnd][lane] = less ? (kept & ~s0) : s0;
-        blk.tmask[cnd][lane + 32] = less ? (kept & ~s1) : s1;
-        if (lane == 0) blk.tmask[cnd][NMS_BLOCK] = less ? kept : 0ull;
+        blk.tmask[cnd][lane] = less ? (all & ~s0) : s0;
+        blk.tmask[cnd][lane + 32] = less ? (all & ~s1) : s1;
+        if (lane == 0) blk.tmask[cnd][NMS_BLOCK] = less ? all : 0ull;
+        const int n_neg = __popc(__ballot_sync(0xffffffffu, k0 == -INFINITY)) + __popc(__ballot_sync(0xffffffffu, k1 == -INFINITY));
+        const int n_pos = __popc(__ballot_sync(0xffffffffu, k0 == INFINITY)) + __popc(__ballot_sync(0xffffffffu, k1 == INFINITY));
+        __syncwarp();
+        if (lane == 0) {
+          float lo = 0.f, hi = 0.f;
+          if (n_neg + n_pos < NMS_BLOCK) { lo = blk.skey[cnd][n_neg]; hi = blk.skey[cnd][NMS_BLOCK - 1 - n_pos]; }
+          const float span = __fsub_rn(hi, lo);
+          const float sc = (span > 0.f && span < INFINITY) ? __fdiv_rn((float)NMS_QB, span) : 0.f;
+          reinterpret_cast<float*>(blk.qlo)[cnd] = lo;
+          reinterpret_cast<float*>(blk.qscale)[cnd] = (sc < INFINITY) ? sc : 0.f;
+        }
       }
+      nms_preparer_barrier();
+      // direct-address tables.  The keys go through the same float function f(k) = (k - qlo) * qscale as the looked-up
+      // values; f is monotone, so k > v implies f(k) >= f(v) >= bucket(v) and k < v implies f(k) <= f(v) < bucket(v) + 1:
+      // qmask[c][b] = {f(key) >= b} for ">" and {f(key) < b + 1} for "<" can never miss a box, whatever the rounding.
+      float* fkey = reinterpret_cast<float*>(s_sort);          // the sort scratch is free again
+#pragma unroll
+      for (int cc = 0; cc < 8 * NMS_BLOCK / NMS_PREPARER_THREADS; ++cc) {
+        const int idx = t + cc * NMS_PREPARER_THREADS, cnd = idx / NMS_BLOCK, pos = idx % NMS_BLOCK;
+        const float lo = reinterpret_cast<const float*>(blk.qlo)[cnd], sc = reinterpret_cast<const float*>(blk.qscale)[cnd];
+        fkey[idx] = __fmul_rn(__fsub_rn(blk.skey[cnd][pos], lo), sc);
+      }
+      nms_preparer_barrier();
+      static_assert(NMS_QB == NMS_PREPARER_THREADS, "one bucket per preparer thread");
+#pragma unroll
+      for (int cnd = 0; cnd < 8; ++cnd) {
+        const bool flat = reinterpret_cast<const float*>(blk.qscale)[cnd] == 0.f;     // no span: every bucket takes all
+        const int b = t;
+        int r;
+        if (cnd & 1) r = (b == NMS_QB - 1 || flat) ? NMS_BLOCK : nms_rank<false>(fkey + cnd * NMS_BLOCK, (float)(b + 1));
+        else r = (b == 0 || flat) ? 0 : nms_rank<false>(fkey + cnd * NMS_BLOCK, (float)b);
+        blk.qmask[cnd][b] = blk.tmask[cnd][r];
+      }
+      nms_preparer_barrier();                                  // fkey is overwritten by the next block's sort keys
+      NMS_TICK(2)
+      // pair mask: box t in the later role against the boxes before it
+      if (have) {
+        unsigned long long todo = (nf ? all : candidates(blk, vx, vy)) & ((1ull << t) - 1ull);
+        while (todo) {
+          const int q = __ffsll((long long)todo) - 1;
+          todo &= todo - 1ull;
+          if (per_class && blk.cls[q] != c) continue;
+          if (pair_suppresses(blk, q, bx, nf)) atomicOr(&blk.pairmask[q], 1ull << t);
+        }
+      }
+      NMS_TICK(3)
     };
 
-    if (tid < NMS_RESOLVER_THREADS) {
-      prepare_block(0, blks[0]);
+    // FINALIZE (threads 0..63): apply the kept boxes of prev (may be null) to the prepared block at c0, then its kept set
+    auto finalize_block = [&](const int c0, SweepBlock<T>& blk, const SweepBlock<T>* prev) {
+      const int nb = min(NMS_BLOCK, K - c0);
+      const int i = c0 + tid;
+      const bool have = tid < nb;
+      long long t_last = clock64();
+      unsigned char f = have ? flags[i] : (unsigned char)1;
+      if (prev != nullptr && have && !(f & 1) && prev->kept != 0ull) {
+        const bool exact_j = (f & 4) != 0;
+        unsigned long long todo = (exact_j ? ~0ull : candidates(*prev, blk.vx[tid], blk.vy[tid])) & prev->kept;
+        bool sup = false;
+        while (todo && !sup) {
+          const int q = __ffsll((long long)todo) - 1;
+          todo &= todo - 1ull;
+          if (per_class && prev->cls[q] != blk.cls[tid]) continue;
+          sup = pair_suppresses(*prev, q, blk.box[tid], exact_j);
+        }
+        if (sup) { f |= 1; flags[i] = f; }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, have && !(f & 1));
+      if (lane == 0) s_alive[warp] = bal;
       nms_resolver_barrier();
-      finalize_block(0, blks[0], nullptr);
-      if (NMS_BLOCK < K) prepare_block(NMS_BLOCK, blks[1]);
+      NMS_TICK(4)
+      // sequential pass over the pair mask in 32-bit halves, the masks fetched eight at a time ahead of the dependent
+      // chain; a box only ever removes later ones, so what is alive at the end is the kept set
+      if (tid == 0) {
+        unsigned alo = s_alive[0], ahi = s_alive[1];
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          unsigned long long m[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) m[u] = blk.pairmask[i0 + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (alo & (1u << (i0 + u))) { alo &= ~(unsigned)m[u]; ahi &= ~(unsigned)(m[u] >> 32); }
+          }
+        }
+        for (int i0 = 32; i0 < 64; i0 += 8) {
+          unsigned mh[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mh[u] = (unsigned)(blk.pairmask[i0 + u] >> 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (ahi & (1u << (i0 + u - 32))) ahi &= ~mh[u];
+          }
+        }
+        blk.kept = ((unsigned long long)ahi << 32) | alo;
+      }
+      nms_resolver_barrier();
+      NMS_TICK(5)
+      if (have && ((blk.kept >> tid) & 1ull)) flags[i] = f | 2;
+    };
+
+    const bool finalizer = tid < NMS_RESOLVER_THREADS, preparer = !finalizer && tid < NMS_RESOLVER_THREADS + NMS_PREPARER_THREADS;
+    if (preparer) {
+      prepare_block(0, blks[0]);
+      if (NMS_BLOCK < K) { nms_preparer_barrier(); prepare_block(NMS_BLOCK, blks[1]); }
     }
     if (tid == 0) { s_next[0] = 0; s_next[1] = 0; }
+    __syncthreads();
+    if (finalizer) finalize_block(0, blks[0], nullptr);
     __syncthreads();
     int bi = 0;                                   // block index modulo 3
     for (int b0 = 0, par = 0; b0 < K; b0 += NMS_BLOCK, par ^= 1, bi = (bi == 2) ? 0 : bi + 1) {
       const SweepBlock<T>& kc = blks[bi];
-      if (tid < NMS_RESOLVER_THREADS) {
-        const int b1 = (bi == 2) ? 0 : bi + 1, b2 = (b1 == 2) ? 0 : b1 + 1;
+      const int b1 = (bi == 2) ? 0 : bi + 1, b2 = (b1 == 2) ? 0 : b1 + 1;
+      if (finalizer) {
         if (b0 + NMS_BLOCK < K) finalize_block(b0 + NMS_BLOCK, blks[b1], &kc);
-        if (b0 + 2 * NMS_BLOCK < K) prepare_block(b0 + 2 * NMS_BLOCK, blks[b2]);
         if (tid == 0) s_next[par ^ 1] = 0;
+      } else if (preparer) {
+        if (b0 + 2 * NMS_BLOCK < K) prepare_block(b0 + 2 * NMS_BLOCK, blks[b2]);
       }
-      if (kc.kept != 0ull) {
+      const unsigned long long kept_c = kc.kept;
+      if (kept_c != 0ull && !(a.debug & 1)) {
         int n2 = 0;                              // entries in the queue (warp-uniform)
         auto decide_entries = [&](const int n) {
           if (lane < n) {
@@ -918,15 +972,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
               int d = 0;
               if (!kc.nf[q]) d = decide_f32(kc.f4[q], kc.f4i[q], kc.area[q], sf4[jj], sf4i[jj], sarea[jj], thr_dn, thr_up);
               hit = d > 0;
-              if (d == 0) {                     // too close to the threshold (or an exact-only kept box): float64
-                const BoxC<T> bl = sb[jj];
-                if (kc.nf[q]) {
-                  const T v = iou_ref<T, true>(kc.box[q], bl);
-                  hit = per_class ? (v > thr) : (v >= thr);
-                } else {
-                  hit = suppresses_finite<T>(kc.box[q], bl, thr, per_class);
-                }
-              }
+              if (d == 0) hit = pair_suppresses(kc, q, sb[jj], false);     // too close to the threshold, or an exact-only kept box
               if (hit) flags[jj] = fjj | 1;     // several lanes may store the same byte: same value
             }
           }
@@ -943,9 +989,20 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
           const bool live = !(fj & 1);
           unsigned long long todo = 0ull;
           if (live && !(fj & 4)) {
-            todo = candidates(kc, skx[j], sky[j]);
+            todo = bucket_candidates(kc, skx[j], sky[j]) & kept_c;
           } else if (live) {
-            if (exact_scan(kc, sb[j], per_class ? scls[j] : 0)) flags[j] = fj | 1;
+            // an exact-only box j (rare): numpy-semantics IoU against every kept box, on this lane alone
+            const BoxC<T> bj = sb[j];
+            const int cj = per_class ? scls[j] : 0;
+            unsigned long long km = kept_c;
+            bool sup = false;
+            while (km && !sup) {
+              const int q = __ffsll((long long)km) - 1;
+              km &= km - 1ull;
+              if (per_class && kc.cls[q] != cj) continue;
+              sup = pair_suppresses(kc, q, bj, true);
+            }
+            if (sup) flags[j] = fj | 1;
           }
           // surviving pairs -> queue, one per lane and round
           while (__any_sync(0xffffffffu, todo != 0ull)) {
@@ -970,6 +1027,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       }
       __syncthreads();
     }
+    if ((a.debug & 2) && img == 0 && tid == NMS_RESOLVER_THREADS)
+      printf("nms prepare (clk, image 0, K=%d): stage %lld  sorts %lld  tables %lld  pairmask %lld\n", K, tm[0], tm[1], tm[2], tm[3]);
+    if ((a.debug & 2) && img == 0 && tid == 0)
+      printf("nms finalize (clk, image 0, K=%d): apply-prev %lld  serial %lld\n", K, tm[4], tm[5]);
+#undef NMS_TICK
   } else {
     // Generic variant (float32 boxes, or a threshold that every pair has to be evaluated for): block after block.
     for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
