@@ -456,6 +456,14 @@ __device__ __forceinline__ void bitonic_sort_desc(KeyPtr keys, int n_pow2) {
   }
 }
 
+// #{k : f(sk[k]) < y} with f(k) = (k - lo) * sc, the bucket function of the direct-address tables
+__device__ __forceinline__ int nms_rank_f(const float* sk, float lo, float sc, float y) {
+  int r = 0;
+#pragma unroll
+  for (int st = NMS_BLOCK / 2; st >= 1; st >>= 1) r += (__fmul_rn(__fsub_rn(sk[r + st - 1], lo), sc) < y) ? st : 0;
+  return r + ((__fmul_rn(__fsub_rn(sk[r], lo), sc) < y) ? 1 : 0);
+}
+
 // Generic sweep: the kept boxes of one block of NMS_BLOCK sorted boxes, compacted.  A non-finite or irregular kept box
 // carries all-covering prefilter corners, so the prefilter never drops it.
 template <typename T>
@@ -768,6 +776,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       return suppresses_finite<T>(blk.box[q], bj, thr, per_class);
     };
 
+    // Direct-address tables of a prepared block, one entry per thread (all warps, at the start of the iteration before the
+    // block is swept with).  The keys go through the same float function f(k) = (k - qlo) * qscale as the looked-up
+    // values; f is monotone, so k > v implies f(k) >= f(v) >= bucket(v) and k < v implies f(k) <= f(v) < bucket(v) + 1:
+    // qmask[c][b] = {f(key) >= b} for ">" and {f(key) < b + 1} for "<" can never miss a box, whatever the rounding.
+    static_assert(NMS_THREADS == 8 * NMS_QB, "one (condition, bucket) entry per thread");
+    auto fill_qmask = [&](SweepBlock<T>& blk) {
+      const int cnd = tid / NMS_QB, b = tid % NMS_QB;
+      const float lo = reinterpret_cast<const float*>(blk.qlo)[cnd], sc = reinterpret_cast<const float*>(blk.qscale)[cnd];
+      const bool flat = sc == 0.f;                              // no span: every bucket takes all
+      int r;
+      if (cnd & 1) r = (b == NMS_QB - 1 || flat) ? NMS_BLOCK : nms_rank_f(blk.skey[cnd], lo, sc, (float)(b + 1));
+      else r = (b == 0 || flat) ? 0 : nms_rank_f(blk.skey[cnd], lo, sc, (float)b);
+      blk.qmask[cnd][b] = blk.tmask[cnd][r];
+    };
+
     // PREPARE (threads 64..191; box t = thread 64 + t): everything about the block at c0 that its geometry alone determines
     auto prepare_block = [&](const int c0, SweepBlock<T>& blk) {
       const int t = tid - NMS_RESOLVER_THREADS, w = warp - NMS_RESOLVER_THREADS / 32;
@@ -852,28 +875,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         }
       }
       nms_preparer_barrier();
-      // direct-address tables.  The keys go through the same float function f(k) = (k - qlo) * qscale as the looked-up
-      // values; f is monotone, so k > v implies f(k) >= f(v) >= bucket(v) and k < v implies f(k) <= f(v) < bucket(v) + 1:
-      // qmask[c][b] = {f(key) >= b} for ">" and {f(key) < b + 1} for "<" can never miss a box, whatever the rounding.
-      float* fkey = reinterpret_cast<float*>(s_sort);          // the sort scratch is free again
-#pragma unroll
-      for (int cc = 0; cc < 8 * NMS_BLOCK / NMS_PREPARER_THREADS; ++cc) {
-        const int idx = t + cc * NMS_PREPARER_THREADS, cnd = idx / NMS_BLOCK, pos = idx % NMS_BLOCK;
-        const float lo = reinterpret_cast<const float*>(blk.qlo)[cnd], sc = reinterpret_cast<const float*>(blk.qscale)[cnd];
-        fkey[idx] = __fmul_rn(__fsub_rn(blk.skey[cnd][pos], lo), sc);
-      }
-      nms_preparer_barrier();
-      static_assert(NMS_QB == NMS_PREPARER_THREADS, "one bucket per preparer thread");
-#pragma unroll
-      for (int cnd = 0; cnd < 8; ++cnd) {
-        const bool flat = reinterpret_cast<const float*>(blk.qscale)[cnd] == 0.f;     // no span: every bucket takes all
-        const int b = t;
-        int r;
-        if (cnd & 1) r = (b == NMS_QB - 1 || flat) ? NMS_BLOCK : nms_rank<false>(fkey + cnd * NMS_BLOCK, (float)(b + 1));
-        else r = (b == 0 || flat) ? 0 : nms_rank<false>(fkey + cnd * NMS_BLOCK, (float)b);
-        blk.qmask[cnd][b] = blk.tmask[cnd][r];
-      }
-      nms_preparer_barrier();                                  // fkey is overwritten by the next block's sort keys
       NMS_TICK(2)
       // pair mask: box t in the later role against the boxes before it
       if (have) {
@@ -948,11 +949,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     if (tid == 0) { s_next[0] = 0; s_next[1] = 0; }
     __syncthreads();
     if (finalizer) finalize_block(0, blks[0], nullptr);
+    fill_qmask(blks[0]);
     __syncthreads();
     int bi = 0;                                   // block index modulo 3
     for (int b0 = 0, par = 0; b0 < K; b0 += NMS_BLOCK, par ^= 1, bi = (bi == 2) ? 0 : bi + 1) {
       const SweepBlock<T>& kc = blks[bi];
       const int b1 = (bi == 2) ? 0 : bi + 1, b2 = (b1 == 2) ? 0 : b1 + 1;
+      if (b0 + 2 * NMS_BLOCK < K) fill_qmask(blks[b1]);        // block b + 1 is swept with only if boxes follow it
       if (finalizer) {
         if (b0 + NMS_BLOCK < K) finalize_block(b0 + NMS_BLOCK, blks[b1], &kc);
         if (tid == 0) s_next[par ^ 1] = 0;
@@ -978,12 +981,25 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
           }
         };
         const int first = b0 + 2 * NMS_BLOCK;
-        while (true) {
+        auto grab = [&]() -> int {
           int g = 0;
           if (lane == 0) g = atomicAdd(&s_next[par], 1);
-          g = __shfl_sync(0xffffffffu, g, 0);
+          return __shfl_sync(0xffffffffu, g, 0);
+        };
+        int g = grab();
+        while (true) {
           const int j0 = first + g * 32;
           if (j0 >= K) break;
+          // the next group is claimed now and its lines are pulled into L1 while this one is worked on
+          g = grab();
+          {
+            const int jn = first + g * 32 + lane;
+            if (jn < K) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(skx + jn));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(sky + jn));
+              if ((lane & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(flags + jn));
+            }
+          }
           const int j = j0 + lane;
           const unsigned char fj = (j < K) ? flags[j] : (unsigned char)1;
           const bool live = !(fj & 1);
