@@ -986,26 +986,24 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
           if (lane == 0) g = atomicAdd(&s_next[par], 1);
           return __shfl_sync(0xffffffffu, g, 0);
         };
+        // software pipeline: the next group is claimed and its flags / lookup values are loaded while this one is worked on
         int g = grab();
-        while (true) {
-          const int j0 = first + g * 32;
-          if (j0 >= K) break;
-          // the next group is claimed now and its lines are pulled into L1 while this one is worked on
-          g = grab();
-          {
-            const int jn = first + g * 32 + lane;
-            if (jn < K) {
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(skx + jn));
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(sky + jn));
-              if ((lane & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(flags + jn));
-            }
-          }
+        int j0 = first + g * 32;
+        unsigned char fj_n = (unsigned char)1;
+        float4 vx_n = make_float4(0.f, 0.f, 0.f, 0.f), vy_n = vx_n;
+        if (j0 + lane < K) { fj_n = flags[j0 + lane]; vx_n = skx[j0 + lane]; vy_n = sky[j0 + lane]; }
+        while (j0 < K) {
           const int j = j0 + lane;
-          const unsigned char fj = (j < K) ? flags[j] : (unsigned char)1;
+          const unsigned char fj = fj_n;
+          const float4 vxj = vx_n, vyj = vy_n;
+          g = grab();
+          j0 = first + g * 32;
+          fj_n = (unsigned char)1;
+          if (j0 + lane < K) { fj_n = flags[j0 + lane]; vx_n = skx[j0 + lane]; vy_n = sky[j0 + lane]; }
           const bool live = !(fj & 1);
           unsigned long long todo = 0ull;
           if (live && !(fj & 4)) {
-            todo = bucket_candidates(kc, skx[j], sky[j]) & kept_c;
+            todo = bucket_candidates(kc, vxj, vyj) & kept_c;
           } else if (live) {
             // an exact-only box j (rare): numpy-semantics IoU against every kept box, on this lane alone
             const BoxC<T> bj = sb[j];
