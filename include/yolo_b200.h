@@ -174,7 +174,10 @@ int yb_engine_autotune(yb_engine* e, int n, int reps);
 int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* needed);
 /* Debug / measurement switches: "pdl" (programmatic dependent launch between convs, default 1), "pairs", "bstat",
  * "tma_epi" (allow those kernel features, default 1), "ablate" (bit mask of roofline probes of the conv kernel:
- * 1 = no epilogue work, 2 = no MMAs, 4 = no activation loads, 8 = no weight loads; outputs are wrong while set). */
+ * 1 = no epilogue work, 2 = no MMAs, 4 = no activation loads, 8 = no weight loads; outputs are wrong while set),
+ * "graph" (CUDA graph of the forward: -1 = automatic, used for batches of at most 32 images, where the 75 launches
+ * rather than the device work bound sess.run of net/yolo.py:83; 0 = never; 1 = always.  A (batch, input buffer, dtype)
+ * combination runs eagerly the first time, is captured the second time and replayed from then on). */
 int yb_engine_set_option(yb_engine* e, const char* name, int value);
 /* Forces the launch configuration of launched op `op_index` (bn = 0 restores the heuristic; bstat / tma_epi: -1 =
  * heuristic, 0 = off, 1 = on when possible; ksub = BK-blocks per pipeline stage, 0 = heuristic) and times one op in isolation (average of reps launches, milliseconds). */
@@ -186,6 +189,8 @@ int yb_engine_time_op(yb_engine* e, int op_index, int n, int reps, float* ms);
 int yb_engine_read_cycles(yb_engine* e, unsigned long long* out16, int reset);
 /* number of kernel launches the last forward / detect enqueued */
 int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_launches);
+/* Number of forwards launched by replaying a captured CUDA graph since the engine was created. */
+int yb_engine_graph_replays(yb_engine* e, int* replays);
 
 /* ---- pipelining, timing and introspection (used by bench.py; optional for integrators) ---- */
 /* Records device event `idx` (0..7) on the engine's stream / returns the device time between two marks

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "yb_engine_time_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
     "yb_engine_read_cycles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_launch_count": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int), _P(ctypes.c_int)]),
+    "yb_engine_graph_replays": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int)]),
     "yb_engine_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_engine_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
     "yb_engine_fetch_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),

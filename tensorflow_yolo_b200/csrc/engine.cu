@@ -470,7 +470,20 @@ struct yb_engine {
   bool detected = false;
   int conv_impl = 0;
   int fwd_launches = 0, det_launches = 0;
+  // CUDA graphs of the forward (one per batch size / input buffer / input dtype).  Small batches are launch-bound:
+  // 75 launches at ~9 us each against a few hundred us of device work.  A key is run eagerly the first time (one-time
+  // attribute calls, autotuned configurations settle), captured the second time, replayed afterwards.
+  struct FwdGraph { int n; const void* input; int dtype; int seen; cudaGraphExec_t exec; };
+  std::vector<FwdGraph> graphs;
+  int graph_mode = -1;            // -1: automatic (n <= YB_GRAPH_AUTO_MAX_N), 0: never, 1: always
+  int graph_replays = 0;
 };
+constexpr int YB_GRAPH_AUTO_MAX_N = 32;
+
+static void clear_graphs(yb_engine* e) {
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
 
 namespace yb {
 
@@ -1265,6 +1278,7 @@ void yb_engine_destroy(yb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  clear_graphs(e);
   for (Op& op : e->ops) { cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift); }
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   cudaFree(e->dbg_counters);
@@ -1286,6 +1300,7 @@ void yb_engine_destroy(yb_engine* e) {
 int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* consumed) {
   if (!e || !stream) return fail(YB_ERR_INVALID, "yb_engine_load_weights: bad argument");
   YB_TRY(set_device(e->device));
+  clear_graphs(e);
   size_t need = 0;
   for (const Op& op : e->ops)
     if (op.kind == OP_CONV) need += (size_t)(e->plan[op.layer].batch_norm ? 4 : 1) * op.cout + (size_t)op.cout * op.cin * op.ksize * op.ksize;
@@ -1344,7 +1359,54 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
 }
 
 // enqueues every op of the plan on the engine's stream; slot >= 0: the input sits in staging buffer `slot`
+// Replays (or captures) the CUDA graph of the forward for this batch size and input buffer.  Returns 1 when the forward
+// was launched through a graph, 0 when the caller has to enqueue the kernels itself, negative on error.
+static int try_graph_forward(yb_engine* e, int n, int slot) {
+  const bool want = e->graph_mode == 1 || (e->graph_mode < 0 && n <= YB_GRAPH_AUTO_MAX_N);
+  if (!want || e->prof_on || e->ablate || e->dbg_counters || e->conv_impl != 0) return 0;
+  yb_engine::FwdGraph* fg = nullptr;
+  for (auto& g : e->graphs) if (g.n == n && g.input == e->cur_input && g.dtype == e->cur_input_dtype) { fg = &g; break; }
+  if (!fg) {
+    if (e->graphs.size() >= 32) clear_graphs(e);
+    e->graphs.push_back({n, e->cur_input, e->cur_input_dtype, 0, nullptr});
+    fg = &e->graphs.back();
+  }
+  if (!fg->exec) {
+    if (fg->seen < 0) return 0;                    // capture failed before: stay eager
+    if (fg->seen++ == 0) return 0;                 // first time: eager
+    if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); fg->seen = -1; return 0; }
+    int rc = YB_OK;
+    for (Op& op : e->ops) { rc = run_op(e, op, n); if (rc != YB_OK) break; }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc != YB_OK || ce != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      fg->seen = -1;
+      return rc != YB_OK ? rc : 0;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess || !exec) { cudaGetLastError(); fg->seen = -1; return 0; }
+    fg->exec = exec;
+  }
+  YB_CUDA(cudaGraphLaunch(fg->exec, e->stream));
+  // the staging buffer is free again once the whole graph has run (coarser than the eager path's event after the last
+  // reader of the input; irrelevant at the batch sizes graphs are used for)
+  if (slot >= 0) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
+  ++e->graph_replays;
+  e->fwd_launches = (int)e->ops.size();
+  e->last_n = n;
+  e->detected = false;
+  return 1;
+}
+
 static int enqueue_ops(yb_engine* e, int n, int slot, cudaEvent_t* evs, int* n_ev) {
+  if (!evs) {
+    const int g = try_graph_forward(e, n, slot);
+    if (g != 0) return g < 0 ? g : YB_OK;
+  }
   e->fwd_launches = 0;
   std::vector<cudaEvent_t> own;
   if (!evs && e->prof_on) {
@@ -1574,6 +1636,7 @@ int yb_engine_profile(yb_engine* e, const void* images, int dtype, int mem, int 
 int yb_engine_set_conv_impl(yb_engine* e, int impl) {
   if (!e || (impl != 0 && impl != 1)) return fail(YB_ERR_INVALID, "yb_engine_set_conv_impl: bad argument");
   e->conv_impl = impl;
+  clear_graphs(e);
   return YB_OK;
 }
 
@@ -1582,7 +1645,10 @@ int yb_engine_autotune(yb_engine* e, int n, int reps) {
   if (n <= 0 || n > e->max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, e->max_batch);
   if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_autotune before yb_engine_load_weights");
   YB_TRY(set_device(e->device));
-  return autotune(e, n, reps > 0 ? reps : 5);
+  clear_graphs(e);
+  const int rc = autotune(e, n, reps > 0 ? reps : 5);
+  clear_graphs(e);                           // the launch configurations changed
+  return rc;
 }
 
 int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* needed) {
@@ -1597,7 +1663,9 @@ int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* need
 
 int yb_engine_set_option(yb_engine* e, const char* name, int value) {
   if (!e || !name) return fail(YB_ERR_INVALID, "yb_engine_set_option: bad argument");
-  if (!strcmp(name, "pdl")) e->pdl = value != 0;
+  clear_graphs(e);                           // every option changes what a captured forward would launch
+  if (!strcmp(name, "graph")) e->graph_mode = value < 0 ? -1 : (value ? 1 : 0);
+  else if (!strcmp(name, "pdl")) e->pdl = value != 0;
   else if (!strcmp(name, "ablate")) e->ablate = value & 15;
   else if (!strcmp(name, "solo_issue")) e->solo_issue = value != 0;
   else if (!strcmp(name, "cycles")) {       // in-kernel cycle counters of the conv roles (read with yb_engine_read_cycles)
@@ -1624,6 +1692,7 @@ int yb_engine_set_conv_cfg(yb_engine* e, int op_index, int bn, int pair, int bst
   if (!e || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_set_conv_cfg: bad argument");
   Op& op = e->ops[op_index];
   if (op.kind != OP_CONV || op.path != PATH_TC) return fail(YB_ERR_INVALID, "op %d is not a tcgen05 conv", op_index);
+  clear_graphs(e);
   if (bn == 0) { op.cfg = default_cfg(op, e->max_batch, e->cta_pairs); return YB_OK; }
   if ((bn != 32 && bn != 64 && bn != 128 && bn != 256) || bn > op.bn_max) return fail(YB_ERR_INVALID, "op %d: N tile %d not available (max %d)", op_index, bn, op.bn_max);
   if (pair && bn < 64) return fail(YB_ERR_INVALID, "op %d: CTA pairs need an N tile of at least 64", op_index);
@@ -1660,6 +1729,12 @@ int yb_engine_launch_count(yb_engine* e, int* forward_launches, int* detect_laun
   if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
   if (forward_launches) *forward_launches = e->fwd_launches;
   if (detect_launches) *detect_launches = e->det_launches;
+  return YB_OK;
+}
+
+int yb_engine_graph_replays(yb_engine* e, int* replays) {
+  if (!e || !replays) return fail(YB_ERR_INVALID, "yb_engine_graph_replays: bad argument");
+  *replays = e->graph_replays;
   return YB_OK;
 }
 

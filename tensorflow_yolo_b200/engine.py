@@ -237,6 +237,12 @@ class Engine(object):
         _lib.check(_lib.lib().yb_engine_launch_count(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def graph_replays(self):
+        """Forwards launched by replaying a captured CUDA graph (set_option("graph", -1 | 0 | 1))."""
+        r = ctypes.c_int()
+        _lib.check(_lib.lib().yb_engine_graph_replays(self._h, ctypes.byref(r)))
+        return r.value
+
     def profile(self, images):
         """[(plan layer index, milliseconds)] per launched op for one forward (CUDA events)."""
         ptr, mem, dt, keep = _buffer(images, (np.dtype(np.float32), np.dtype(np.uint8)))

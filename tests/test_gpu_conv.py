@@ -216,3 +216,46 @@ def test_autotune_keeps_results_bit_identical():
         eng.set_option("no_such_option", 1)
     assert eng.time_op(tc_ops[0], 3, 2) > 0.0
     eng.close()
+
+
+def test_cuda_graph_forward_is_bit_identical_and_replayed():
+    """Small batches replay a captured CUDA graph of the 75 launches (eager the first time a (batch, input buffer, dtype)
+    is seen, captured the second time): the outputs and the detections must equal the eager path's bit for bit, for host
+    inputs (two staging buffers -> two graphs), device inputs, uint8 inputs and a different batch size in between."""
+    import torch
+    shape = (96, 64, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=2, obj_bias=-1.0)
+    x = synth.images(3, shape[0], shape[1], seed=5)
+    x8 = (x * 255).astype(np.uint8)
+    eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 3, stream)
+    eng.set_option("graph", 0)
+    eng.forward(x)
+    y0 = eng.read_output()
+    d0 = eng.detect(0.5, 0.6)
+    eng.forward(x8)
+    y8 = eng.read_output()
+    eng.forward(x[:2])
+    y2 = eng.read_output()
+    assert eng.graph_replays() == 0
+    eng.set_option("graph", -1)                # automatic: batch 3 <= 32
+    xd = torch.from_numpy(x).cuda()
+    for it in range(6):
+        eng.forward(x)                         # host input: staging buffers alternate
+        assert np.array_equal(eng.read_output(), y0), it
+        d = eng.detect(0.5, 0.6)
+        assert all(np.array_equal(a["row"], b["row"]) for a, b in zip(d, d0))
+        eng.forward(xd)                        # device input: one more key
+        assert np.array_equal(eng.read_output(), y0), it
+        eng.forward(x[:2])
+        assert np.array_equal(eng.read_output(), y2), it
+        eng.forward(x8)
+        assert np.array_equal(eng.read_output(), y8), it
+    assert eng.graph_replays() >= 12
+    fwd, _ = eng.launch_count()
+    assert fwd == 75
+    # a configuration change drops the captured graphs; results stay the same
+    n_before = eng.graph_replays()
+    eng.set_option("pdl", 0)
+    eng.forward(xd)
+    assert np.array_equal(eng.read_output(), y0) and eng.graph_replays() == n_before
+    eng.close()
