@@ -557,6 +557,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int it = 0;
     int epi_idx = 0;            // running sub-tile counter of this warp (selects the staging buffer)
     uint32_t res_par = 0;       // phase bits of this warp's two residual barriers
+    bool res_ahead = false;     // the residual of this warp's next sub-tile is already on its way (TMA epilogue)
     griddep_wait();             // residual reads and output stores must follow the previous kernels
     const bool dbg = pa.dbg != nullptr;
     long long t_acc = 0, t_res = 0, t_buf = 0, t_ld = 0, t_math = 0, t_fs = 0;
@@ -618,7 +619,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           mbar_expect_tx(&rbar[b], CONV_TCP_EPI_BUF);
           tma_load_2d(&tmRes, &rbar[b], bufs + b * CONV_TCP_EPI_BUF, n0 + chunk * 32, m_warp);
         };
-        if (has_res_t && ch_begin < ch_end && lane == 0) issue_res(ch_begin, epi_idx);
+        // the first chunk's residual was requested at the end of this warp's previous tile (res_ahead), except for its
+        // first tile: a narrow tile has one chunk per warp, so a request made here would expose the full memory latency
+        if (has_res_t && ch_begin < ch_end && !res_ahead && lane == 0) issue_res(ch_begin, epi_idx);
+        if (ch_begin < ch_end) res_ahead = false;
         long long t0 = dbg ? clk() : 0;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (dbg) t_acc += clk() - t0;
@@ -712,6 +716,22 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tma_store_commit();
           }
           if (dbg) t_fs += clk() - t0;
+        }
+        if (has_res_t && ch_begin < ch_end) {
+          // residual of the first chunk of this warp's next tile, into the buffer the store before last has left
+          const int nt = tile + ((NCH == 1) ? 2 : 1) * walk_step;
+          if (nt < pa.n_tiles) {
+            if (lane == 0) {
+              const int nmj = nt / pa.n_tiles_n;
+              const int nm = (PAIR ? 2 * nmj + (int)rank : nmj) * 128 + quarter * 32;
+              const int nn0 = (nt - nmj * pa.n_tiles_n) * BN + ((NCH == 1) ? 0 : ch_begin0) * 32;
+              const int b = epi_idx & 1;
+              tma_store_wait_read<1>();
+              mbar_expect_tx(&rbar[b], CONV_TCP_EPI_BUF);
+              tma_load_2d(&tmRes, &rbar[b], bufs + b * CONV_TCP_EPI_BUF, nn0, nm);
+            }
+            res_ahead = true;
+          }
         }
         tc_fence_before();
         __syncwarp();
