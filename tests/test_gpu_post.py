@@ -285,3 +285,45 @@ def test_nms_dense_config5_image_vs_oracle():
     c = helpers.cand_from_dets(cand[0])
     assert len(c["row"]) == 10647
     assert np.array_equal(c["row"][postprocess.nms(c, 0.6)], kept[0]["row"])
+
+
+def test_decode_class_argmax_near_ties():
+    """np.argmax(sigmoid(t)) with classes a few float32 ulps apart, equal, saturated (sigmoid == 1 for many classes) and
+    tiny (subnormal sigmoids): the device ranks classes on 1 + exp(-t) with the fast exponential and has to fall back to the
+    exact quotients whenever that ranking cannot be trusted; the first of the maxima wins, as in numpy."""
+    shape = (64, 64, 3)
+    post = _post_v3(shape, 2)
+    rs = np.random.RandomState(11)
+    R = 252
+    head = np.zeros((2, R, 85), np.float32)
+    head[..., :4] = rs.normal(0, 1, (2, R, 4))
+    head[..., 4] = 3.0                                               # every row is a candidate
+    base = rs.choice([-95.0, -60.0, -20.0, -3.0, 0.0, 2.5, 9.0, 17.0, 40.0, 90.0], size=(2, R, 1)).astype(np.float32)
+    cls = np.broadcast_to(base, (2, R, 80)).copy()
+    kind = rs.randint(0, 4, size=(2, R))
+    for i in range(2):
+        for r in range(R):
+            row = cls[i, r]
+            if kind[i, r] == 0:                                      # a handful of classes within a few ulps of the top
+                top = rs.choice(80, 5, replace=False)
+                row -= np.float32(abs(row[0]) * 1e-3 + 1e-3)
+                for j, k in enumerate(top):
+                    v = np.float32(base[i, r, 0])
+                    for _ in range(int(rs.randint(0, 4))):
+                        v = np.nextafter(v, np.float32(-np.inf))
+                    row[k] = v
+            elif kind[i, r] == 1:                                    # all equal: class 0
+                pass
+            elif kind[i, r] == 2:                                    # relative differences around the tie band
+                row += (rs.choice([1e-7, 1e-6, 1e-5, 1e-4, 1e-3], 80) * rs.normal(0, 1, 80) * max(1.0, abs(float(row[0])))).astype(np.float32)
+            else:                                                    # ordinary logits
+                row[:] = rs.normal(0, 3, 80)
+    head[..., 5:] = cls
+    cands = post.decode(head, 0.5)
+    for i in range(2):
+        ref = postprocess.decode_v3_image(head[i], _geo(shape), 0.5)
+        c = helpers.cand_from_dets(cands[i])
+        assert np.array_equal(c["row"], ref["row"]) and len(c["row"]) == R
+        bad = np.nonzero(c["class_idx"] != ref["class_idx"])[0]
+        assert bad.size == 0, [(int(r), int(kind[i, r]), float(base[i, r, 0]), int(c["class_idx"][r]), int(ref["class_idx"][r]))
+                               for r in bad[:8]]
