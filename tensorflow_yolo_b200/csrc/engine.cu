@@ -294,6 +294,13 @@ struct Op {
   // conv
   int cout = 0, cout_pad = 0, cin = 0, ksize = 0, stride = 1, pad = 0, leaky = 0, has_res = 0, out_mode = 0;
   int Ho = 0, Wo = 0, path = PATH_TC, bn_max = 0, bk = 0;
+  // Pixel-pair view (px_pair = 1): a stride-1 conv with 32 input channels is launched as the same conv over PAIRS of
+  // horizontally adjacent pixels -- [N,H,W,32] read as [N,H,W/2,64], [N,H,W,Cout] written as [N,H,W/2,2*Cout], the
+  // weights re-packed with structural zeros (load_weights).  Same bytes, same results bit for bit (the extra products
+  // are exact zeros added to an fp32 sum), but 128-byte im2col rows instead of 64-byte ones -- the TMA engine delivers
+  // about one row per 2-3 cycles whatever its length -- and an N tile twice as wide, which an M=128 MMA gets for free.
+  // cin / cout / Wo and the views below then describe the paired problem.
+  int px_pair = 0;
   ConvCfg cfg;
   int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0;   // what the last launch resolved to
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
@@ -435,6 +442,7 @@ struct yb_engine {
   bool cta_pairs = true;
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
   bool fuse_upsample = true;    // conv epilogue writes the 2x2 replicas itself (YB_FUSE_UPSAMPLE=0: separate copy kernel)
+  bool pixel_pairs = true;      // Op::px_pair for the Cin=32 stride-1 convs (YB_PIXEL_PAIRS=0: plain view)
   int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
   int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
   unsigned long long* dbg_counters = nullptr;   // device [CONV_DBG_COUNT] cycle counters while "cycles" is switched on
@@ -877,6 +885,16 @@ static int compile_plan(yb_engine* e) {
                           (l.ksize == 1 || l.ksize == 3) && (l.stride == 1 || l.stride == 2) &&
                           (op.out.f32 || (op.cout % 8 == 0 && op.out.ld % 8 == 0 && op.out.coff % 8 == 0)) &&
                           (!op.has_res || (op.in2.ld % 8 == 0 && op.in2.coff % 8 == 0));
+      if (e->pixel_pairs && tma_ok && op.cin == 32 && l.stride == 1 && op.out_mode == OUT_PLAIN && !op.out.f32 &&
+          op.cout % 32 == 0 && op.cout <= 128 && op.Wo % 2 == 0 && op.in.w == op.Wo && op.in.ld == op.cin && op.in.coff == 0 &&
+          op.out.ld == op.cout && op.out.coff == 0 && (!op.has_res || (op.in2.ld == op.cout && op.in2.coff == 0 && op.in2.w == op.Wo))) {
+        op.px_pair = 1;
+        op.Wo /= 2;
+        op.in.w /= 2; op.in.c *= 2; op.in.ld *= 2;
+        op.out.w /= 2; op.out.c *= 2; op.out.ld *= 2;
+        if (op.has_res) { op.in2.w /= 2; op.in2.c *= 2; op.in2.ld *= 2; }
+        op.cin *= 2; op.cout *= 2;
+      }
       if (op.in.f32 || op.in.buf == -2) {
         if (op.cin > 8) return fail(YB_ERR_INVALID, "layer %d: fp32 conv input with %d channels is not supported", i, op.cin);
         op.path = PATH_DIRECT;
@@ -1231,6 +1249,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   e->keep_all = ka && atoi(ka) != 0;
   const char* fu = getenv("YB_FUSE_UPSAMPLE");
   if (fu) e->fuse_upsample = atoi(fu) != 0;
+  const char* pp = getenv("YB_PIXEL_PAIRS");
+  if (pp) e->pixel_pairs = atoi(pp) != 0;
   const char* pd = getenv("YB_PDL");
   if (pd) e->pdl = atoi(pd) != 0;
   const char* cp = getenv("YB_PAIR");
@@ -1303,7 +1323,10 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
   clear_graphs(e);
   size_t need = 0;
   for (const Op& op : e->ops)
-    if (op.kind == OP_CONV) need += (size_t)(e->plan[op.layer].batch_norm ? 4 : 1) * op.cout + (size_t)op.cout * op.cin * op.ksize * op.ksize;
+    if (op.kind == OP_CONV) {
+      const size_t co = op.px_pair ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin;     // the file's dimensions
+      need += (size_t)(e->plan[op.layer].batch_norm ? 4 : 1) * co + co * ci * op.ksize * op.ksize;
+    }
   if (n < need) {
     if (consumed) *consumed = 0;
     return fail(YB_ERR_SHORT_WEIGHTS, "weight stream has %zu floats, the plan needs %zu", n, need);
@@ -1313,7 +1336,8 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
   std::vector<float> packed32, scale, shift;
   for (Op& op : e->ops) {
     if (op.kind != OP_CONV) continue;
-    const int co = op.cout, ci = op.cin, k = op.ksize, K = k * k * ci;
+    // co, ci: the file's dimensions; a pixel-pair op packs them into twice the channels on either side
+    const int co = op.px_pair ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin, k = op.ksize, K = k * k * ci;
     const bool bn = e->plan[op.layer].batch_norm != 0;
     scale.assign(op.cout_pad, 0.0f); shift.assign(op.cout_pad, 0.0f);
     if (bn) {   // stream order: beta, gamma, moving_mean, moving_variance (net/layers.py:53-63)
@@ -1328,6 +1352,7 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
       for (int o = 0; o < co; ++o) { scale[o] = 1.0f; shift[o] = stream[read + o]; }
       read += co;
     }
+    if (op.px_pair) for (int o = 0; o < co; ++o) { scale[co + o] = scale[o]; shift[co + o] = shift[o]; }   // both pixels of a pair
     const float* kern = stream + read;   // [O][I][kh][kw] (net/base.py:36-40)
     read += (size_t)co * K;
     cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift);
@@ -1339,6 +1364,25 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
           for (int t = 0; t < k * k; ++t) packed32[(size_t)(t * ci + i) * co + o] = kern[((size_t)o * ci + i) * k * k + t];
       YB_CUDA(cudaMalloc(&op.d_wt32, packed32.size() * 4));
       YB_CUDA(cudaMemcpy(op.d_wt32, packed32.data(), packed32.size() * 4, cudaMemcpyHostToDevice));
+    } else if (op.px_pair) {
+      // Paired problem: output channel eo * co + o (eo = pixel of the output pair), input channel ei * ci + i, tap
+      // (ky, kp) with kp the offset in pairs.  Output pixel 2q + eo reads input pixel 2(q + kp - pad) + ei, i.e. the
+      // original tap kx = 2 (kp - pad) + ei - eo + pad; the combinations that fall outside the kernel stay zero.
+      const int K2 = k * k * 2 * ci, pad = (k - 1) / 2;
+      packed.assign((size_t)op.cout_pad * K2, 0);
+      for (int eo = 0; eo < 2; ++eo)
+        for (int o = 0; o < co; ++o)
+          for (int ky = 0; ky < k; ++ky)
+            for (int kp = 0; kp < k; ++kp)
+              for (int ei = 0; ei < 2; ++ei) {
+                const int kx = 2 * (kp - pad) + ei - eo + pad;
+                if (kx < 0 || kx >= k) continue;
+                for (int i = 0; i < ci; ++i)
+                  packed[(size_t)(eo * co + o) * K2 + (size_t)(ky * k + kp) * 2 * ci + ei * ci + i] =
+                      f32_to_bf16_rne(kern[((size_t)o * ci + i) * k * k + ky * k + kx]);
+              }
+      YB_CUDA(cudaMalloc(&op.d_wt, packed.size() * 2));
+      YB_CUDA(cudaMemcpy(op.d_wt, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
     } else {
       packed.assign((size_t)op.cout_pad * K, 0);
       for (int o = 0; o < co; ++o)
@@ -1809,7 +1853,8 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   if (bn_tile) *bn_tile = op.cfg.bn;
   if (bk) *bk = op.bk;
   if (stages) *stages = op.launched_stages;
-  if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin : 0.0;
+  // a pixel-pair op multiplies twice the useful products (half of its packed weights are structural zeros)
+  if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin / (op.px_pair ? 2.0 : 1.0) : 0.0;
   return YB_OK;
 }
 

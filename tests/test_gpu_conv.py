@@ -259,3 +259,23 @@ def test_cuda_graph_forward_is_bit_identical_and_replayed():
     eng.forward(xd)
     assert np.array_equal(eng.read_output(), y0) and eng.graph_replays() == n_before
     eng.close()
+
+
+def test_pixel_pair_view_is_bit_identical(monkeypatch):
+    """The Cin=32 stride-1 3x3 conv (layer 4, +residual) is launched over pairs of pixels with zero-padded weights
+    (YB_PIXEL_PAIRS, default on): same bytes in and out, and -- the extra products being exact zeros -- the same bits."""
+    shape = (128, 160, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=4)
+    x = synth.images(3, shape[0], shape[1], seed=5)
+    got = {}
+    monkeypatch.setenv("YB_KEEP_ALL", "1")
+    for flag in ("1", "0"):
+        monkeypatch.setenv("YB_PIXEL_PAIRS", flag)
+        eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 3, stream)
+        eng.forward(x)
+        got[flag] = (eng.read_layer(5)[0], eng.read_output(), eng.op_cfg(3)["bn"])     # layer 5 = conv 4 + shortcut
+        eng.close()
+    assert got["1"][2] == 128 and got["0"][2] == 64            # the paired problem has twice the output channels
+    for a, b in zip(got["1"][:2], got["0"][:2]):
+        assert np.array_equal(a, b)
+    assert helpers.rel_err(got["1"][1], convstack.forward(topo, stream, x)) <= TOL

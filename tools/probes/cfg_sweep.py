@@ -22,7 +22,7 @@ for op in ops:
     base = eng.time_op(op, B, reps=20)
     print("op", op, "default", eng.op_cfg(op), "%.4f ms" % base)
     rows = []
-    for bn, pair, bstat, tma_epi, ksub in itertools.product((32, 64), (0, 1), (0, 1), (0, 1), (1, 3, 9)):
+    for bn, pair, bstat, tma_epi, ksub in itertools.product((32, 64, 128), (0, 1), (0, 1), (0, 1), (1, 3, 9)):
         try:
             eng.set_conv_cfg(op, bn, pair, bstat, tma_epi, ksub)
             ms = min(eng.time_op(op, B, reps=20) for _ in range(2))
