@@ -326,11 +326,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const InView in, const _
   for (int kh = 0; kh < a.ksize; ++kh) {
     const int y = p * a.conv_stride + kh - a.pad;
     if (y < 0 || y >= in.H) continue;
-    for (int kw = 0; kw < a.ksize; ++kw) {
-      const int xx = q * a.conv_stride + kw - a.pad;
+    for (int kw = 0; kw < a.kw; ++kw) {
+      const int xx = q * a.stride_w + kw - a.pad_w;
       if (xx < 0 || xx >= in.W) continue;
       const uint16_t* xp = x + (((long long)img * in.H + y) * in.W + xx) * in.ld;
-      const int kbase = (kh * a.ksize + kw) * in.C;
+      const int kbase = (kh * a.kw + kw) * in.C;
       for (int ci = 0; ci < in.C; ++ci) {
         const float v = bf16_bits_to_f32(xp[ci]);
 #pragma unroll

@@ -36,8 +36,11 @@ struct ConvArgs {
   int M;              // valid output pixels = n * Ho * Wo
   int Ho, Wo;         // output spatial size
   int cout;           // real output channels
-  int taps;           // ksize*ksize
-  int ksize;
+  int taps;           // ksize * kw
+  int ksize;          // kernel height
+  int kw;             // kernel width   } differ from ksize / conv_stride / pad only for the input-pair view of a stride-2 conv
+  int stride_w;       // stride along W } (engine.cu, Op::px_pair == 2)
+  int pad_w;          // low-side padding along W
   int kc_blocks;      // Cin / BK
   int conv_stride;    // 1 or 2
   int pad;            // low-side padding ((k-1)/2)
@@ -414,7 +417,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             img = m0 / hw;
             const int rem = m0 - img * hw;
             const int p0 = rem / a.Wo;
-            base_w = (rem - p0 * a.Wo) * a.conv_stride - a.pad;
+            base_w = (rem - p0 * a.Wo) * a.stride_w - a.pad_w;
             base_h = p0 * a.conv_stride - a.pad;
           }
           int cb = 0, kh = 0, kw = 0;
@@ -447,7 +450,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
                 if (load_b) tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n0);
               }
-              if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.ksize) { kw = 0; ++kh; } }
+              if (++cb == a.kc_blocks) { cb = 0; if (++kw == a.kw) { kw = 0; ++kh; } }
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }

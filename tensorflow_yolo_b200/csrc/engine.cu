@@ -131,13 +131,16 @@ static int make_tiled_map(CUtensorMap* tm, const void* base, long long rows, int
 
 // activation [N,H,W,C] bf16 (pixel pitch ld) as an im2col map: 128 output pixels x bk channels per load
 static int make_im2col_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int ld, int ksize, int stride,
-                           int pad_lo, int bk) {
+                           int pad_lo, int bk, int kw = 0, int stride_w = 0, int pad_w = -1) {
+  if (kw <= 0) kw = ksize;
+  if (stride_w <= 0) stride_w = stride;
+  if (pad_w < 0) pad_w = pad_lo;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  const int pad_hi = (ksize - 1) - pad_lo;
-  int lower[2] = {-pad_lo, -pad_lo};                               // {W, H}: offset of the first window's origin
-  int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};     // far corner: last window origin relative to the edge
-  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  const int pad_hi = (ksize - 1) - pad_lo, pad_hi_w = (kw - 1) - pad_w;
+  int lower[2] = {-pad_w, -pad_lo};                                // {W, H}: offset of the first window's origin
+  int upper[2] = {pad_hi_w - (kw - 1), pad_hi - (ksize - 1)};      // far corner: last window origin relative to the edge
+  cuuint32_t es[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                                (cuuint32_t)bk, 128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -300,7 +303,12 @@ struct Op {
   // are exact zeros added to an fp32 sum), but 128-byte im2col rows instead of 64-byte ones -- the TMA engine delivers
   // about one row per 2-3 cycles whatever its length -- and an N tile twice as wide, which an M=128 MMA gets for free.
   // cin / cout / Wo and the views below then describe the paired problem.
+  // px_pair = 2: the stride-2 3x3 conv with 32 input channels reads its INPUT in pairs ([N,H,W/2,64]); output pixel x
+  // needs input pixels 2x-1, 2x, 2x+1 = the second pixel of pair x-1 and both of pair x, i.e. a 3 (high) x 2 (wide) kernel
+  // over pairs with stride (2, 1) and padding 1 on the left only.  Six 128-byte im2col rows per pixel instead of nine
+  // 64-byte ones; the output side is unchanged.
   int px_pair = 0;
+  int kw = 0, stride_w = 0, pad_w = 0;      // kernel width, stride and low padding along W (= ksize, stride, pad unless px_pair == 2)
   ConvCfg cfg;
   int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0;   // what the last launch resolved to
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
@@ -442,7 +450,8 @@ struct yb_engine {
   bool cta_pairs = true;
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
   bool fuse_upsample = true;    // conv epilogue writes the 2x2 replicas itself (YB_FUSE_UPSAMPLE=0: separate copy kernel)
-  bool pixel_pairs = true;      // Op::px_pair for the Cin=32 stride-1 convs (YB_PIXEL_PAIRS=0: plain view)
+  int pixel_pairs = 1;          // Op::px_pair: 1 = the Cin=32 stride-1 convs (default), 2 = also the stride-2 one (measured
+                                // slower: 0.423 -> 0.441 ms, K grows by a third), 0 = plain views (YB_PIXEL_PAIRS)
   int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
   int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
   unsigned long long* dbg_counters = nullptr;   // device [CONV_DBG_COUNT] cycle counters while "cycles" is switched on
@@ -614,7 +623,7 @@ static ConvCfg default_cfg(const Op& op, int max_batch, bool allow_pair) {
   ConvCfg c;
   c.bn = op.bn_max;
   const long long M = (long long)max_batch * op.Ho * op.Wo;
-  const int K = op.ksize * op.ksize * op.cin;
+  const int K = op.ksize * op.kw * op.cin;
   c.pair = (allow_pair && c.bn >= 64 && M > 128 && op.bk == 64 && (op.ksize > 1 || (c.bn == 256 && K >= 512))) ? 1 : 0;
   return c;
 }
@@ -645,7 +654,8 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
   if (op.kind == OP_CONV) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.M = n * op.Ho * op.Wo; a.Ho = op.Ho; a.Wo = op.Wo; a.cout = op.cout; a.taps = op.ksize * op.ksize; a.ksize = op.ksize;
+    a.M = n * op.Ho * op.Wo; a.Ho = op.Ho; a.Wo = op.Wo; a.cout = op.cout; a.taps = op.ksize * op.kw; a.ksize = op.ksize;
+    a.kw = op.kw; a.stride_w = op.stride_w; a.pad_w = op.pad_w;
     a.conv_stride = op.stride; a.pad = op.pad; a.scale = op.d_scale; a.shift = op.d_shift; a.leaky = op.leaky;
     a.res = op.has_res ? reinterpret_cast<const __nv_bfloat16*>(view_ptr(e, op.in2)) : nullptr;
     a.res_ld = op.in2.ld;
@@ -878,6 +888,7 @@ static int compile_plan(yb_engine* e) {
       op.out = e->view[dst];
       op.cin = e->shape[l.src[0]].c; op.cout = l.filters; op.ksize = l.ksize; op.stride = l.stride;
       op.pad = (l.ksize - 1) / 2; op.leaky = l.leaky; op.out_mode = out_mode[i];
+      op.kw = op.ksize; op.stride_w = op.stride; op.pad_w = op.pad;
       op.Ho = e->shape[i].h; op.Wo = e->shape[i].w;
       if (res_src[i] >= 0) { op.has_res = 1; op.in2 = e->view[res_src[i]]; if (op.in2.buf == -1 || op.in2.f32) return fail(YB_ERR_INVALID, "layer %d: bad residual source", i); }
       const bool in_bf16 = !op.in.f32;
@@ -894,6 +905,13 @@ static int compile_plan(yb_engine* e) {
         op.out.w /= 2; op.out.c *= 2; op.out.ld *= 2;
         if (op.has_res) { op.in2.w /= 2; op.in2.c *= 2; op.in2.ld *= 2; }
         op.cin *= 2; op.cout *= 2;
+      }
+      if (e->pixel_pairs >= 2 && !op.px_pair && tma_ok && op.cin == 32 && l.ksize == 3 && l.stride == 2 && op.in.w % 2 == 0 &&
+          op.in.w == 2 * op.Wo && op.in.ld == op.cin && op.in.coff == 0) {
+        op.px_pair = 2;
+        op.in.w /= 2; op.in.c *= 2; op.in.ld *= 2;
+        op.cin *= 2;
+        op.kw = 2; op.stride_w = 1; op.pad_w = 1;
       }
       if (op.in.f32 || op.in.buf == -2) {
         if (op.cin > 8) return fail(YB_ERR_INVALID, "layer %d: fp32 conv input with %d channels is not supported", i, op.cin);
@@ -998,9 +1016,10 @@ static int build_tensor_maps(yb_engine* e) {
     if (op.ksize == 1 && op.stride == 1) {
       YB_TRY(make_tiled_map(&op.tmA, in_ptr, (long long)e->max_batch * op.in.h * op.in.w, op.cin, op.in.ld, 128, op.bk));
     } else {
-      YB_TRY(make_im2col_map(&op.tmA, in_ptr, e->max_batch, op.in.h, op.in.w, op.cin, op.in.ld, op.ksize, op.stride, op.pad, op.bk));
+      YB_TRY(make_im2col_map(&op.tmA, in_ptr, e->max_batch, op.in.h, op.in.w, op.cin, op.in.ld, op.ksize, op.stride, op.pad, op.bk,
+                             op.kw, op.stride_w, op.pad_w));
     }
-    const int K = op.ksize * op.ksize * op.cin;
+    const int K = op.ksize * op.kw * op.cin;
     memset(op.tmB, 0, sizeof(op.tmB));
     for (int bn = 32; bn <= op.bn_max; bn <<= 1) YB_TRY(make_tiled_map(&op.tmB[bn_index(bn)], op.d_wt, op.cout_pad, K, K, bn, op.bk));
     // TMA epilogue (plain bf16 outputs): 32 rows x 32 channels per store, 64-byte swizzle
@@ -1131,7 +1150,7 @@ static int autotune(yb_engine* e, int n, int reps) {
     }
     // second pass: BK-blocks per stage for the best configuration found so far
     {
-      const int num_k = op.ksize * op.ksize * (op.cin / op.bk);
+      const int num_k = op.ksize * op.kw * (op.cin / op.bk);
       const int ks[] = {1, 2, 3, 4, 6, 9};
       ConvCfg base = best_cfg;
       for (int k : ks) {
@@ -1250,7 +1269,7 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   const char* fu = getenv("YB_FUSE_UPSAMPLE");
   if (fu) e->fuse_upsample = atoi(fu) != 0;
   const char* pp = getenv("YB_PIXEL_PAIRS");
-  if (pp) e->pixel_pairs = atoi(pp) != 0;
+  if (pp) e->pixel_pairs = atoi(pp);
   const char* pd = getenv("YB_PDL");
   if (pd) e->pdl = atoi(pd) != 0;
   const char* cp = getenv("YB_PAIR");
@@ -1324,7 +1343,7 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
   size_t need = 0;
   for (const Op& op : e->ops)
     if (op.kind == OP_CONV) {
-      const size_t co = op.px_pair ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin;     // the file's dimensions
+      const size_t co = op.px_pair == 1 ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin;     // the file's dimensions
       need += (size_t)(e->plan[op.layer].batch_norm ? 4 : 1) * co + co * ci * op.ksize * op.ksize;
     }
   if (n < need) {
@@ -1337,7 +1356,7 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
   for (Op& op : e->ops) {
     if (op.kind != OP_CONV) continue;
     // co, ci: the file's dimensions; a pixel-pair op packs them into twice the channels on either side
-    const int co = op.px_pair ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin, k = op.ksize, K = k * k * ci;
+    const int co = op.px_pair == 1 ? op.cout / 2 : op.cout, ci = op.px_pair ? op.cin / 2 : op.cin, k = op.ksize, K = k * k * ci;
     const bool bn = e->plan[op.layer].batch_norm != 0;
     scale.assign(op.cout_pad, 0.0f); shift.assign(op.cout_pad, 0.0f);
     if (bn) {   // stream order: beta, gamma, moving_mean, moving_variance (net/layers.py:53-63)
@@ -1352,7 +1371,7 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
       for (int o = 0; o < co; ++o) { scale[o] = 1.0f; shift[o] = stream[read + o]; }
       read += co;
     }
-    if (op.px_pair) for (int o = 0; o < co; ++o) { scale[co + o] = scale[o]; shift[co + o] = shift[o]; }   // both pixels of a pair
+    if (op.px_pair == 1) for (int o = 0; o < co; ++o) { scale[co + o] = scale[o]; shift[co + o] = shift[o]; }   // both pixels of a pair
     const float* kern = stream + read;   // [O][I][kh][kw] (net/base.py:36-40)
     read += (size_t)co * K;
     cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift);
@@ -1364,7 +1383,24 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
           for (int t = 0; t < k * k; ++t) packed32[(size_t)(t * ci + i) * co + o] = kern[((size_t)o * ci + i) * k * k + t];
       YB_CUDA(cudaMalloc(&op.d_wt32, packed32.size() * 4));
       YB_CUDA(cudaMemcpy(op.d_wt32, packed32.data(), packed32.size() * 4, cudaMemcpyHostToDevice));
-    } else if (op.px_pair) {
+    } else if (op.px_pair == 2) {
+      // Input pairs only (stride 2): tap (ky, kp), kp = 0 / 1 the pair left of / at the output pixel, input channel
+      // ei * ci + i; output pixel x reads input pixel 2 (x + kp - 1) + ei = 2x + kx - 1, i.e. kx = 2 kp + ei - 1.
+      const int K2 = k * 2 * 2 * ci;
+      packed.assign((size_t)op.cout_pad * K2, 0);
+      for (int o = 0; o < co; ++o)
+        for (int ky = 0; ky < k; ++ky)
+          for (int kp = 0; kp < 2; ++kp)
+            for (int ei = 0; ei < 2; ++ei) {
+              const int kx = 2 * kp + ei - 1;
+              if (kx < 0 || kx >= k) continue;
+              for (int i = 0; i < ci; ++i)
+                packed[(size_t)o * K2 + (size_t)(ky * 2 + kp) * 2 * ci + ei * ci + i] =
+                    f32_to_bf16_rne(kern[((size_t)o * ci + i) * k * k + ky * k + kx]);
+            }
+      YB_CUDA(cudaMalloc(&op.d_wt, packed.size() * 2));
+      YB_CUDA(cudaMemcpy(op.d_wt, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    } else if (op.px_pair == 1) {
       // Paired problem: output channel eo * co + o (eo = pixel of the output pair), input channel ei * ci + i, tap
       // (ky, kp) with kp the offset in pairs.  Output pixel 2q + eo reads input pixel 2(q + kp - pad) + ei, i.e. the
       // original tap kx = 2 (kp - pad) + ei - eo + pad; the combinations that fall outside the kernel stay zero.
@@ -1854,6 +1890,7 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   if (bk) *bk = op.bk;
   if (stages) *stages = op.launched_stages;
   // a pixel-pair op multiplies twice the useful products (half of its packed weights are structural zeros)
+  // (px_pair == 2: the 3 x 2 kernel over 64 channels holds the 3 x 3 x 32 useful products)
   if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin / (op.px_pair ? 2.0 : 1.0) : 0.0;
   return YB_OK;
 }

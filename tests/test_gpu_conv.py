@@ -262,20 +262,25 @@ def test_cuda_graph_forward_is_bit_identical_and_replayed():
 
 
 def test_pixel_pair_view_is_bit_identical(monkeypatch):
-    """The Cin=32 stride-1 3x3 conv (layer 4, +residual) is launched over pairs of pixels with zero-padded weights
-    (YB_PIXEL_PAIRS, default on): same bytes in and out, and -- the extra products being exact zeros -- the same bits."""
+    """The Cin=32 3x3 convs can be launched over pairs of pixels with zero-padded weights (YB_PIXEL_PAIRS): layer 4 (stride 1,
+    +residual) with both sides paired (1, the default), layer 2 (stride 2) with the input side paired and 3 x 2 taps (2,
+    measured slower and therefore off).  Same bytes in and out, and -- the extra products being exact zeros, the K walk
+    visiting the real ones in the same order -- the same bits."""
     shape = (128, 160, 3)
     net, topo, stream = helpers.build_v3(shape, 80, seed=4)
     x = synth.images(3, shape[0], shape[1], seed=5)
     got = {}
     monkeypatch.setenv("YB_KEEP_ALL", "1")
-    for flag in ("1", "0"):
+    for flag in ("2", "1", "0"):
         monkeypatch.setenv("YB_PIXEL_PAIRS", flag)
         eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 3, stream)
         eng.forward(x)
-        got[flag] = (eng.read_layer(5)[0], eng.read_output(), eng.op_cfg(3)["bn"])     # layer 5 = conv 4 + shortcut
+        # layer 2 = the stride-2 conv, layer 5 = conv 4 + shortcut
+        got[flag] = (eng.read_layer(2)[0], eng.read_layer(5)[0], eng.read_output(), eng.op_cfg(3)["bn"], eng.op_info(1)["bk"])
         eng.close()
-    assert got["1"][2] == 128 and got["0"][2] == 64            # the paired problem has twice the output channels
-    for a, b in zip(got["1"][:2], got["0"][:2]):
-        assert np.array_equal(a, b)
-    assert helpers.rel_err(got["1"][1], convstack.forward(topo, stream, x)) <= TOL
+    assert [got[f][3] for f in "210"] == [128, 128, 64]         # the paired problem has twice the output channels
+    assert [got[f][4] for f in "210"] == [64, 32, 32]           # ... and 64 input channels per K block
+    for flag in ("2", "1"):
+        for a, b in zip(got[flag][:3], got["0"][:3]):
+            assert np.array_equal(a, b)
+    assert helpers.rel_err(got["1"][2], convstack.forward(topo, stream, x)) <= TOL
