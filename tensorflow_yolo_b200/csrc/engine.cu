@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/yolo_b200.h"
@@ -362,10 +363,19 @@ struct PreCtx {
   ResizeImage* d_imgs[2] = {nullptr, nullptr};
   ResizeTab* d_tabs[2] = {nullptr, nullptr};
   size_t imgs_cap[2] = {0, 0}, tabs_cap[2] = {0, 0};
-  std::vector<unsigned char> pinned_dummy;
+  // Pinned staging of the caller's (pageable) images: a few host threads gather them into page-locked memory, chunk by
+  // chunk, and each chunk goes out as one DMA while the next is gathered.  A cudaMemcpyAsync straight from pageable memory
+  // runs at ~10 GB/s and blocks the caller for its whole length (128 decoded 720p frames: 34 ms per step against 9 ms of
+  // compute).
+  unsigned char* pinned[2] = {nullptr, nullptr};
+  size_t pinned_cap[2] = {0, 0};
 
   void release() {
-    for (int i = 0; i < 2; ++i) { cudaFree(raw[i]); cudaFree(d_imgs[i]); cudaFree(d_tabs[i]); raw[i] = nullptr; d_imgs[i] = nullptr; d_tabs[i] = nullptr; raw_cap[i] = imgs_cap[i] = tabs_cap[i] = 0; }
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(raw[i]); cudaFree(d_imgs[i]); cudaFree(d_tabs[i]); raw[i] = nullptr; d_imgs[i] = nullptr; d_tabs[i] = nullptr; raw_cap[i] = imgs_cap[i] = tabs_cap[i] = 0;
+      if (pinned[i]) cudaFreeHost(pinned[i]);
+      pinned[i] = nullptr; pinned_cap[i] = 0;
+    }
   }
 
   // Uploads n BGR images (host memory) on copy stream `cs`, builds their tables and enqueues the resize kernel on `ks`
@@ -391,9 +401,38 @@ struct PreCtx {
     std::vector<ResizeTab> tabs;
     struct Key { int sh, sw, xtab, ytab; };
     std::vector<Key> seen;
+    // upload: small batches straight from the caller's memory, large ones through the pinned staging buffer
+    const bool staged = total >= ((size_t)4 << 20);
+    if (staged) {
+      if (total > pinned_cap[slot]) {
+        if (pinned[slot]) cudaFreeHost(pinned[slot]);
+        pinned[slot] = nullptr; pinned_cap[slot] = 0;
+        YB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pinned[slot]), total + total / 4, cudaHostAllocDefault));
+        pinned_cap[slot] = total + total / 4;
+      }
+      // pinned[slot] is free: the DMAs of its previous use were synchronised at the end of that call
+      const unsigned hc = std::thread::hardware_concurrency();
+      const int n_thr = (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+      const int n_chunks = std::min(n, 4);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = (int)((long long)n * c / n_chunks), i1 = (int)((long long)n * (c + 1) / n_chunks);
+        auto gather = [&](int t) {
+          for (int i = i0 + t; i < i1; i += n_thr) {
+            const int stride = strides ? strides[i] : widths[i] * 3;
+            memcpy(pinned[slot] + offs[i], images[i], (size_t)heights[i] * stride);
+          }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr && i0 + t < i1; ++t) pool.emplace_back(gather, t);
+        gather(0);
+        for (auto& th : pool) th.join();
+        const size_t b0 = offs[i0], b1 = (i1 < n) ? offs[i1] : total;
+        YB_CUDA(cudaMemcpyAsync(raw[slot] + b0, pinned[slot] + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+      }
+    }
     for (int i = 0; i < n; ++i) {
       const int stride = strides ? strides[i] : widths[i] * 3;
-      YB_CUDA(cudaMemcpyAsync(raw[slot] + offs[i], images[i], (size_t)heights[i] * stride, cudaMemcpyHostToDevice, cs));
+      if (!staged) YB_CUDA(cudaMemcpyAsync(raw[slot] + offs[i], images[i], (size_t)heights[i] * stride, cudaMemcpyHostToDevice, cs));
       ResizeImage& im = imgs[i];
       im.src = raw[slot] + offs[i]; im.sh = heights[i]; im.sw = widths[i]; im.stride = stride;
       im.area2x = (widths[i] == 2 * dw && heights[i] == 2 * dh) ? 1 : 0;
