@@ -369,10 +369,12 @@ struct PreCtx {
   // compute).
   unsigned char* pinned[2] = {nullptr, nullptr};
   size_t pinned_cap[2] = {0, 0};
+  cudaEvent_t pin_done[2] = {nullptr, nullptr};   // the DMAs out of pinned[i] have completed
 
   void release() {
     for (int i = 0; i < 2; ++i) {
       cudaFree(raw[i]); cudaFree(d_imgs[i]); cudaFree(d_tabs[i]); raw[i] = nullptr; d_imgs[i] = nullptr; d_tabs[i] = nullptr; raw_cap[i] = imgs_cap[i] = tabs_cap[i] = 0;
+      if (pin_done[i]) { cudaEventSynchronize(pin_done[i]); cudaEventDestroy(pin_done[i]); pin_done[i] = nullptr; }
       if (pinned[i]) cudaFreeHost(pinned[i]);
       pinned[i] = nullptr; pinned_cap[i] = 0;
     }
@@ -404,13 +406,15 @@ struct PreCtx {
     // upload: small batches straight from the caller's memory, large ones through the pinned staging buffer
     const bool staged = total >= ((size_t)4 << 20);
     if (staged) {
+      // the DMAs of this buffer's previous use (two calls ago) must have read it
+      if (!pin_done[slot]) YB_CUDA(cudaEventCreateWithFlags(&pin_done[slot], cudaEventDisableTiming));
+      else YB_CUDA(cudaEventSynchronize(pin_done[slot]));
       if (total > pinned_cap[slot]) {
         if (pinned[slot]) cudaFreeHost(pinned[slot]);
         pinned[slot] = nullptr; pinned_cap[slot] = 0;
         YB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pinned[slot]), total + total / 4, cudaHostAllocDefault));
         pinned_cap[slot] = total + total / 4;
       }
-      // pinned[slot] is free: the DMAs of its previous use were synchronised at the end of that call
       const unsigned hc = std::thread::hardware_concurrency();
       const int n_thr = (int)std::max(1u, std::min(8u, hc ? hc : 1u));
       const int n_chunks = std::min(n, 4);
@@ -429,6 +433,7 @@ struct PreCtx {
         const size_t b0 = offs[i0], b1 = (i1 < n) ? offs[i1] : total;
         YB_CUDA(cudaMemcpyAsync(raw[slot] + b0, pinned[slot] + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
       }
+      YB_CUDA(cudaEventRecord(pin_done[slot], cs));
     }
     for (int i = 0; i < n; ++i) {
       const int stride = strides ? strides[i] : widths[i] * 3;
@@ -463,7 +468,8 @@ struct PreCtx {
     // descriptors and tables are small: synchronous copies from these temporaries on the copy stream
     YB_CUDA(cudaMemcpyAsync(d_imgs[slot], imgs.data(), (size_t)n * sizeof(ResizeImage), cudaMemcpyHostToDevice, cs));
     YB_CUDA(cudaMemcpyAsync(d_tabs[slot], tabs.data(), tabs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice, cs));
-    YB_CUDA(cudaStreamSynchronize(cs));          // the host vectors die at return; pageable copies have completed anyway
+    // No synchronisation: the descriptor and table vectors are pageable, so those copies have left host memory when the
+    // calls return, and the images were either copied the same way or gathered into the pinned buffer above.
     YB_CUDA(cudaEventRecord(ev, cs));
     YB_CUDA(cudaStreamWaitEvent(ks, ev, 0));
     dim3 grid(ceil_div(dw, 128), dh, n);
