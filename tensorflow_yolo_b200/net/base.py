@@ -279,19 +279,45 @@ def generate_test_batch(img_paths, batch_size, input_shape):
 def generate_raw_batch(img_paths, batch_size):
     """Like generate_test_batch, but yields the decoded BGR uint8 images as cv2.imread returns them: resize, BGR->RGB
     and /255 then run on the GPU (yb_engine_forward_raw), bit-identical to preprocess_image.  An unreadable file ends
-    the run like in the reference (preprocess_image prints and returns None, which its caller cannot unpack)."""
+    the run like in the reference (preprocess_image prints and returns None, which its caller cannot unpack) -- when its
+    batch is reached, not earlier.
+
+    Decoding is the slowest stage of the TEST path once the network runs on the GPU (a few milliseconds per JPEG on one
+    core against 70 microseconds per image for everything else), so the files of a batch are decoded by a thread pool
+    (cv2.imread releases the GIL; YB_DECODE_THREADS, default min(8, cores)) and the next batch is decoded while the
+    caller works on the current one.  Order and batch boundaries are the reference's."""
+    import concurrent.futures
     import cv2
     total_batches = int(np.ceil(len(img_paths) / batch_size))
-    for b in range(total_batches):
-        images, paths = [], []
-        for path in img_paths[b * batch_size:(b + 1) * batch_size]:
-            image = cv2.imread(path)
-            if image is None:
-                print("Failed to read {}".format(path))
-                raise TypeError("cannot unpack non-iterable NoneType object")
-            images.append(image)
-            paths.append(path)
-        yield images, paths
+    n_thr = int(os.environ.get("YB_DECODE_THREADS", str(min(8, os.cpu_count() or 1))))
+    if n_thr <= 1:
+        for b in range(total_batches):
+            images, paths = [], []
+            for path in img_paths[b * batch_size:(b + 1) * batch_size]:
+                image = cv2.imread(path)
+                if image is None:
+                    print("Failed to read {}".format(path))
+                    raise TypeError("cannot unpack non-iterable NoneType object")
+                images.append(image)
+                paths.append(path)
+            yield images, paths
+        return
+    with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
+        def submit(b):
+            paths = list(img_paths[b * batch_size:(b + 1) * batch_size])
+            return paths, [pool.submit(cv2.imread, p) for p in paths]
+        ahead = submit(0) if total_batches > 0 else None
+        for b in range(total_batches):
+            paths, futures = ahead
+            ahead = submit(b + 1) if b + 1 < total_batches else None
+            images = []
+            for path, fut in zip(paths, futures):
+                image = fut.result()
+                if image is None:
+                    print("Failed to read {}".format(path))
+                    raise TypeError("cannot unpack non-iterable NoneType object")
+                images.append(image)
+            yield images, paths
 
 
 def non_maximum_suppression(boxes, iou_threshold):

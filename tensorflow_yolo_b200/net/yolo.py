@@ -82,7 +82,7 @@ class Yolo(object):
                 return "{}: Found {} objects. Saved to {}".format(file_name, len(boxes), out_path)
 
             pending = []
-            with concurrent.futures.ThreadPoolExecutor(max_workers=int(os.environ.get("YB_DRAW_THREADS", "4"))) as pool:
+            with concurrent.futures.ThreadPoolExecutor(max_workers=int(os.environ.get("YB_DRAW_THREADS", str(min(8, os.cpu_count() or 1))))) as pool:
                 for net_boxes, paths in batches:
                     for boxes, path in zip(net_boxes, paths):
                         results[path] = boxes

@@ -171,3 +171,31 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
     src = open(os.path.join(ROOT, "launcher.py")).read()
     assert "oracle" not in src
+
+
+def test_generate_raw_batch_threaded_order_and_late_failure(tmp_path, monkeypatch, capsys, lib_built):
+    """Files are decoded by a thread pool one batch ahead: same order, same batch boundaries as the reference's
+    generate_test_batch (net/base.py:158-168), and an unreadable file ends the run only when its batch is reached."""
+    import cv2
+    from tensorflow_yolo_b200.net import base as pbase
+    rs = np.random.RandomState(3)
+    paths = []
+    for i in range(7):
+        p = str(tmp_path / ("im%02d.png" % i))
+        cv2.imwrite(p, rs.randint(0, 256, size=(20 + i, 30, 3)).astype(np.uint8))
+        paths.append(p)
+    for threads in ("1", "4"):
+        monkeypatch.setenv("YB_DECODE_THREADS", threads)
+        got = list(pbase.generate_raw_batch(paths, 3))
+        assert [len(b[0]) for b in got] == [3, 3, 1] and [p for _, ps in got for p in ps] == paths
+        for imgs, ps in got:
+            for im, p in zip(imgs, ps):
+                assert np.array_equal(im, cv2.imread(p))
+        bad = paths[:4] + [str(tmp_path / "missing.png")] + paths[4:]
+        gen = pbase.generate_raw_batch(bad, 3)
+        first = next(gen)                                   # the first batch is delivered although batch 2 will fail
+        assert first[1] == paths[:3]
+        with pytest.raises(TypeError):
+            next(gen)
+        assert "Failed to read" in capsys.readouterr().out
+    assert list(pbase.generate_raw_batch([], 3)) == []
