@@ -202,7 +202,7 @@ __device__ __forceinline__ void conv_first_mma_body(const InView& in, const floa
     // ---- stage rows y0-1 .. y0+FIRST_ROWS, converting to bf16: four elements per thread and step (16-byte loads
     // of float input, 4-byte loads of uint8 input), all loads of a thread independent of each other ----
     const int quads = row_in >> 2;                   // host guarantees row_in % 4 == 0
-    if (U8 && (row_in & 15) == 0) {
+    if (U8 && (row_in & 15) == 0 && (reinterpret_cast<uintptr_t>(in.ptr) & 15) == 0) {
       // uint8 rows that are a whole number of 16-byte words: 16 elements per load (0.474 -> 0.454 ms per 128 images).
       // float(b) * fl(1/255) differs from the feed's float(b / 255.) by an ulp for half of the byte values, but never
       // after the rounding to bf16 (all 256 values checked; tests: u8 input == float input, bit for bit).
