@@ -569,12 +569,28 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   const float* prob = a.prob + base;
   const int tid = threadIdx.x;
 
-  // ---- 1. count candidates ----
+  // ---- 1 + 2. one pass over the dense scores: count the candidates and build their keys
+  // (orderable score << 32) | (0xFFFFFFFF - row); then sort descending ----
+  unsigned long long* gkeys = a.keys + (long long)img * a.rows_pow2;     // only dereferenced beyond NMS_SMEM_KEYS candidates
   if (tid == 0) s_count = 0;
   __syncthreads();
-  int local = 0;
-  for (int r = tid; r < R; r += NMS_THREADS) { const float pr = prob[r]; local += (pr == pr) ? 1 : 0; }
-  if (local) atomicAdd(&s_count, local);
+  for (int r0 = 0; r0 < R; r0 += 4 * NMS_THREADS) {
+    float pr4[4];                                  // four independent loads in flight before the (ordered) atomics
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NMS_THREADS + tid;
+      pr4[u] = (r < R) ? prob[r] : __int_as_float(0x7fc00000);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pr4[u] == pr4[u]) {
+        const int r = r0 + u * NMS_THREADS + tid;
+        const int pos = atomicAdd(&s_count, 1);
+        const unsigned long long key = ((unsigned long long)orderable(pr4[u]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)r);
+        if (pos < NMS_SMEM_KEYS) s_keys[pos] = key; else gkeys[pos] = key;
+      }
+    }
+  }
   __syncthreads();
   const int K = s_count;
   if (tid == 0) { a.n_cand[img] = K; }
@@ -585,20 +601,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   int P = 1;
   while (P < K) P <<= 1;
   const bool in_smem = (P <= NMS_SMEM_KEYS);
-  unsigned long long* gkeys = a.keys + (long long)img * a.rows_pow2;
-  __syncthreads();
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  // ---- 2. build keys: (orderable score << 32) | (0xFFFFFFFF - row); sort descending ----
-  for (int r0 = 0; r0 < R; r0 += NMS_THREADS) {
-    const int r = r0 + tid;
-    const float pr_ = (r < R) ? prob[r] : __int_as_float(0x7fc00000);
-    const bool v = (pr_ == pr_);
-    if (v) {
-      const int pos = atomicAdd(&s_count, 1);
-      const unsigned long long key = ((unsigned long long)orderable(prob[r]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)r);
-      if (in_smem) s_keys[pos] = key; else gkeys[pos] = key;
-    }
+  if (!in_smem) {          // more candidates than the shared-memory sort holds: everything moves to the global scratch
+    for (int i = tid; i < NMS_SMEM_KEYS; i += NMS_THREADS) gkeys[i] = s_keys[i];
   }
   for (int i = K + tid; i < P; i += NMS_THREADS) {
     if (in_smem) s_keys[i] = 0ull; else gkeys[i] = 0ull;
@@ -740,7 +744,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     if (tid == 0) out.nkept = __popcll(kept);
   };
 
-  if (use_f32) {
+  if (use_f32 && K > NMS_BLOCK) {
     // Pipelined variant (float64 boxes, positive threshold: the engine's regime).  While all warps sweep the boxes after
     // block b + 1 with the kept boxes of block b,
     //   warps 0-1 FINALIZE block b + 1: apply the kept boxes of block b to it, then the sequential greedy pass over its
@@ -1057,7 +1061,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
       printf("nms finalize (clk, image 0, K=%d): apply-prev %lld  serial %lld\n", K, tm[4], tm[5]);
 #undef NMS_TICK
   } else {
-    // Generic variant (float32 boxes, or a threshold that every pair has to be evaluated for): block after block.
+    // Generic variant (float32 boxes, a threshold that every pair has to be evaluated for, or at most one block of
+    // candidates -- the usual case on real images, where the tables of the pipelined variant would never be looked up):
+    // block after block.
     for (int b0 = 0; b0 < K; b0 += NMS_BLOCK) {
       if (tid < NMS_RESOLVER_THREADS) resolve_block(b0, nullptr, s_kb);
       __syncthreads();
