@@ -416,7 +416,8 @@ struct PreCtx {
         pinned_cap[slot] = total + total / 4;
       }
       const unsigned hc = std::thread::hardware_concurrency();
-      const int n_thr = (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+      const char* gt = getenv("YB_GATHER_THREADS");
+      const int n_thr = gt ? std::max(1, atoi(gt)) : (int)std::max(1u, std::min(16u, hc ? hc : 1u));
       const int n_chunks = std::min(n, 4);
       for (int c = 0; c < n_chunks; ++c) {
         const int i0 = (int)((long long)n * c / n_chunks), i1 = (int)((long long)n * (c + 1) / n_chunks);
