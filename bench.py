@@ -305,7 +305,7 @@ def run_ours(args):
     classes, conv_ms, conv_flops, other_ms = {}, 0.0, 0.0, 0.0
     for op_i, (layer, ms_sum) in enumerate(prof):
         info = eng.op_info(op_i)
-        if info["path"] == 0:
+        if info["path"] in (0, 3):            # tcgen05 convs (3: a fused pair, conv_fused.cuh -- FLOPs of both layers)
             spec = state.graph.specs[layer]
             cfg = eng.op_cfg(op_i)
             key = (spec.shape, spec.ksize, spec.stride, state.graph.specs[spec.src[0]].shape[2], info["bn"], info["bk"], cfg["pair"])

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyolo_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["conv_tc.cuh", "aux_kernels.cuh", "post.cuh", os.path.join("..", "..", "include", "yolo_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "yolo_b200.h")]
 
 
 def _nvcc():

@@ -21,6 +21,7 @@
 #include "../../include/yolo_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_tc.cuh"
+#include "conv_fused.cuh"
 #include "post.cuh"
 #include "preprocess.cuh"
 
@@ -280,7 +281,8 @@ struct Buf {
   bool keep = false;
 };
 enum OpKind { OP_CONV = 0, OP_MAXPOOL, OP_ADD, OP_UPSAMPLE, OP_REORG, OP_COPY };
-enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2 };
+enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2, PATH_FUSED = 3 };
+enum FuseKind { FUSE_NONE = 0, FUSE_STEM = 1, FUSE_BLOCK = 2 };
 
 // How one tcgen05 conv is launched.  compile_plan fills in a heuristic; yb_engine_autotune replaces it with the
 // fastest measured candidate.
@@ -310,12 +312,18 @@ struct Op {
   // 64-byte ones; the output side is unchanged.
   int px_pair = 0;
   int kw = 0, stride_w = 0, pad_w = 0;      // kernel width, stride and low padding along W (= ksize, stride, pad unless px_pair == 2)
+  // Two-layer fusion (conv_fused.cuh): this op is the 3x3 consumer conv and also computes its producer conv
+  // ops[fuse_src] (which is then never launched: skip) -- FUSE_STEM: first conv 3->32 + 3x3 s2 32->64;
+  // FUSE_BLOCK: 1x1 64->32 + 3x3 s1 32->64 + shortcut.
+  int fuse_kind = FUSE_NONE, fuse_src = -1;
+  bool skip = false;
   ConvCfg cfg;
   int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0;   // what the last launch resolved to
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
   __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
   alignas(64) CUtensorMap tmA, tmOut, tmRes;
+  alignas(64) CUtensorMap tmOut4;           // fused ops: output as (C, W, H, N), box 32 x 16 x 2 x 1
   alignas(64) CUtensorMap tmB[4];           // weight maps with box rows 32, 64, 128, 256 (128 doubles as the pair half)
   bool tma_epi = false;
   // generic
@@ -496,6 +504,8 @@ struct yb_engine {
   bool cta_pairs = true;
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
   bool fuse_upsample = true;    // conv epilogue writes the 2x2 replicas itself (YB_FUSE_UPSAMPLE=0: separate copy kernel)
+  int fuse_stem = 1, fuse_block = 1;   // conv_fused.cuh (YB_FUSE_STEM / YB_FUSE_BLOCK: 0 = off, 1 = on unless YB_KEEP_ALL, 2 = always)
+  int first_resident[2] = {1, 1};      // co-resident blocks per SM of conv_first_mma_kernel<float / uint8>
   int pixel_pairs = 1;          // Op::px_pair: 1 = the Cin=32 stride-1 convs (default), 2 = also the stride-2 one (measured
                                 // slower: 0.423 -> 0.441 ms, K grows by a third), 0 = plain views (YB_PIXEL_PAIRS)
   int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
@@ -615,11 +625,7 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
   if (pa.n_stages < 2) return fail(YB_ERR_INVALID, "persistent conv: shared memory too small for BN=%d BK=%d", BN, BK);
   const int smem = 1024 + CONV_TCP_HEADER + (pa.tma_epi ? CONV_TCP_EPI_BYTES : 0) + (pa.b_stationary ? (int)b_total : 0) +
                    pa.n_stages * stage_bytes;
-  static unsigned long long attr_done = 0ull;      // per device: the opt-in shared-memory limit is set once
-  if (env.device >= 64 || !((attr_done >> env.device) & 1ull)) {
-    YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
-    if (env.device < 64) attr_done |= 1ull << env.device;
-  }
+  // (the opt-in shared-memory limit of every instantiation is raised once per engine: set_kernel_attrs)
   op.launched_stages = pa.n_stages; op.launched_bstat = pa.b_stationary; op.launched_tma_epi = pa.tma_epi; op.launched_ksub = pa.ksub;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
@@ -695,8 +701,61 @@ static std::vector<ConvCfg> candidate_cfgs(const Op& op, int n, bool allow_pair)
   return v;
 }
 
+// conv_fused.cuh: one persistent CTA per SM over 8 x 16 output tiles
+static int launch_fused(yb_engine* e, Op& op, int n) {
+  const Op& pp = e->ops[op.fuse_src];
+  FuseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_img = n; a.Ho = op.Ho; a.Wo = op.Wo; a.H = pp.in.h; a.W = pp.in.w;
+  a.in = view_ptr(e, pp.in); a.in_ld = pp.in.ld;
+  a.scale1 = pp.d_scale; a.shift1 = pp.d_shift; a.scale2 = op.d_scale; a.shift2 = op.d_shift;
+  a.leaky1 = pp.leaky; a.leaky2 = op.leaky;
+  a.tiles_h = op.Ho / FUSE_TH; a.tiles_w = op.Wo / FUSE_TW; a.n_tiles = n * a.tiles_h * a.tiles_w;
+  const int grid = std::min(a.n_tiles, e->num_sms);
+  const CUtensorMap& tmB = op.tmB[bn_index(FUSE_COUT)];
+  if (op.fuse_kind == FUSE_STEM) {
+    a.w1 = pp.d_wt32;
+    if (e->cur_input_dtype == YB_U8) stem_fused_kernel<true><<<grid, FUSE_THREADS, FUSE_SMEM_STEM, e->stream>>>(tmB, op.tmOut4, a);
+    else stem_fused_kernel<false><<<grid, FUSE_THREADS, FUSE_SMEM_STEM, e->stream>>>(tmB, op.tmOut4, a);
+  } else {
+    a.w1 = pp.d_wt;
+    block_fused_kernel<<<grid, FUSE_THREADS, FUSE_SMEM_BLOCK, e->stream>>>(tmB, op.tmOut4, a);
+  }
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+template <int BN, int BK, bool PAIR>
+static int set_tcp_attr() {
+  YB_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<BN, BK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
+  return YB_OK;
+}
+// Per-device function attributes (opt-in shared-memory limits) and occupancy figures, set when an engine is created on
+// the device -- no process-global bookkeeping, so engines on several devices can be driven from several threads.
+static int set_kernel_attrs(yb_engine* e) {
+  YB_TRY((set_tcp_attr<256, 64, true>())); YB_TRY((set_tcp_attr<128, 64, true>())); YB_TRY((set_tcp_attr<64, 64, true>()));
+  YB_TRY((set_tcp_attr<128, 32, true>())); YB_TRY((set_tcp_attr<64, 32, true>()));
+  YB_TRY((set_tcp_attr<256, 64, false>())); YB_TRY((set_tcp_attr<128, 64, false>())); YB_TRY((set_tcp_attr<64, 64, false>()));
+  YB_TRY((set_tcp_attr<32, 64, false>())); YB_TRY((set_tcp_attr<128, 32, false>())); YB_TRY((set_tcp_attr<64, 32, false>()));
+  YB_TRY((set_tcp_attr<32, 32, false>()));
+  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
+  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
+  YB_CUDA(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_BLOCK));
+  const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2;
+  if (smem_first <= 200 * 1024) {
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[0], conv_first_mma_kernel<false>, 256, smem_first));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[1], conv_first_mma_kernel<true>, 256, smem_first));
+    for (int i = 0; i < 2; ++i) if (e->first_resident[i] < 1) e->first_resident[i] = 1;
+  }
+  return YB_OK;
+}
+
 static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nullptr) {
   cudaStream_t st = e->stream;
+  if (op.skip) return YB_OK;                    // computed inside its consumer (Op::fuse_kind)
+  if (op.kind == OP_CONV && op.path == PATH_FUSED) return launch_fused(e, op, n);
   if (op.kind == OP_CONV) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -725,13 +784,7 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
       if (mma_ok) {
         const int groups = n * ceil_div(op.Ho, FIRST_ROWS);     // stride 1: output rows == input rows
         auto launch = [&](auto kern) -> int {
-          static int resident[2][64] = {{0}};                   // per kernel variant and device: co-resident blocks per SM
-          int& res = resident[u8 ? 1 : 0][e->device < 64 ? e->device : 63];
-          if (res == 0) {
-            YB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, kern, 256, smem_first));
-            if (res < 1) res = 1;
-          }
+          const int res = e->first_resident[u8 ? 1 : 0];          // co-resident blocks per SM (set_kernel_attrs)
           // exactly one resident wave: the blocks walk the row groups with a grid stride, a partial second wave
           // would run at a fraction of the occupancy
           dim3 grid(std::min(groups, e->num_sms * res / std::max(1, op.cout / 32)), op.cout / 32);
@@ -942,6 +995,34 @@ static int compile_plan(yb_engine* e) {
                           (l.ksize == 1 || l.ksize == 3) && (l.stride == 1 || l.stride == 2) &&
                           (op.out.f32 || (op.cout % 8 == 0 && op.out.ld % 8 == 0 && op.out.coff % 8 == 0)) &&
                           (!op.has_res || (op.in2.ld % 8 == 0 && op.in2.coff % 8 == 0));
+      // ---- two-layer fusion (conv_fused.cuh): this 3x3 conv over 32 channels also computes the conv that feeds it ----
+      const bool fuse_shape = tma_ok && l.ksize == 3 && op.cin == 32 && op.cout == FUSE_COUT && op.out_mode == OUT_PLAIN && !op.out.f32 &&
+                              op.Ho % FUSE_TH == 0 && op.Wo % FUSE_TW == 0 && !e->ops.empty() && e->ops.back().kind == OP_CONV &&
+                              e->ops.back().layer == l.src[0] && consumers[l.src[0]].size() == 1 && !e->ops.back().skip &&
+                              e->ops.back().out_mode == OUT_PLAIN && !e->ops.back().has_res && e->ops.back().cout == FUSE_CMID;
+      if (fuse_shape) {
+        Op& pp = e->ops.back();
+        const bool stem = l.stride == 2 && !op.has_res && pp.path == PATH_DIRECT && pp.ksize == 3 && pp.stride == 1 && pp.cin == 3 &&
+                          pp.in.buf == -2 && pp.in.ld == 3 && pp.in.h == 2 * op.Ho && pp.in.w == 2 * op.Wo &&
+                          (e->fuse_stem == 2 || (e->fuse_stem == 1 && !e->keep_all));
+        const bool block = l.stride == 1 && op.has_res && pp.path == PATH_TC && pp.ksize == 1 && pp.stride == 1 && pp.cin == 64 &&
+                           !pp.px_pair && !pp.in.f32 && pp.in.buf >= 0 && pp.in.ld % 8 == 0 && pp.in.coff % 8 == 0 &&
+                           op.in2.buf == pp.in.buf && op.in2.coff == pp.in.coff && op.in2.ld == pp.in.ld &&
+                           (e->fuse_block == 2 || (e->fuse_block == 1 && !e->keep_all));
+        if (stem || block) {
+          op.fuse_kind = stem ? FUSE_STEM : FUSE_BLOCK;
+          op.fuse_src = (int)e->ops.size() - 1;
+          pp.skip = true;
+          if (pp.out.buf >= 0) { e->bufs[pp.out.buf].first = INT_MAX; e->bufs[pp.out.buf].last = -1; }   // never materialised
+          e->view[pp.layer].buf = -1;
+          op.in = pp.in;
+        }
+      }
+      if (op.fuse_kind) {
+        op.path = PATH_FUSED;
+        op.bk = FUSE_CMID; op.bn_max = FUSE_COUT;
+        op.cfg = ConvCfg(); op.cfg.bn = FUSE_COUT;
+      } else
       if (e->pixel_pairs && tma_ok && op.cin == 32 && l.stride == 1 && op.out_mode == OUT_PLAIN && !op.out.f32 &&
           op.cout % 32 == 0 && op.cout <= 128 && op.Wo % 2 == 0 && op.in.w == op.Wo && op.in.ld == op.cin && op.in.coff == 0 &&
           op.out.ld == op.cout && op.out.coff == 0 && (!op.has_res || (op.in2.ld == op.cout && op.in2.coff == 0 && op.in2.w == op.Wo))) {
@@ -952,14 +1033,16 @@ static int compile_plan(yb_engine* e) {
         if (op.has_res) { op.in2.w /= 2; op.in2.c *= 2; op.in2.ld *= 2; }
         op.cin *= 2; op.cout *= 2;
       }
-      if (e->pixel_pairs >= 2 && !op.px_pair && tma_ok && op.cin == 32 && l.ksize == 3 && l.stride == 2 && op.in.w % 2 == 0 &&
+      if (e->pixel_pairs >= 2 && !op.px_pair && !op.fuse_kind && tma_ok && op.cin == 32 && l.ksize == 3 && l.stride == 2 && op.in.w % 2 == 0 &&
           op.in.w == 2 * op.Wo && op.in.ld == op.cin && op.in.coff == 0) {
         op.px_pair = 2;
         op.in.w /= 2; op.in.c *= 2; op.in.ld *= 2;
         op.cin *= 2;
         op.kw = 2; op.stride_w = 1; op.pad_w = 1;
       }
-      if (op.in.f32 || op.in.buf == -2) {
+      if (op.fuse_kind) {
+        // path, tile and weight packing were fixed above (plain [cout][9*32] bf16 weights, N tile 64, BK 32)
+      } else if (op.in.f32 || op.in.buf == -2) {
         if (op.cin > 8) return fail(YB_ERR_INVALID, "layer %d: fp32 conv input with %d channels is not supported", i, op.cin);
         op.path = PATH_DIRECT;
       } else if (tma_ok) {
@@ -973,7 +1056,7 @@ static int compile_plan(yb_engine* e) {
       } else {
         op.path = PATH_SIMT;
       }
-      op.cout_pad = round_up(op.cout, op.path == PATH_TC ? op.bn_max : 4);
+      op.cout_pad = round_up(op.cout, (op.path == PATH_TC || op.path == PATH_FUSED) ? op.bn_max : 4);
       emit = true;
     } else if (l.kind == YB_MAXPOOL) {
       op.kind = OP_MAXPOOL; op.in = e->view[l.src[0]]; op.out = e->view[i]; emit = true;
@@ -1057,6 +1140,20 @@ static int compile_plan(yb_engine* e) {
 
 static int build_tensor_maps(yb_engine* e) {
   for (Op& op : e->ops) {
+    if (op.kind == OP_CONV && op.path == PATH_FUSED) {
+      const int K = 9 * FUSE_CMID;
+      memset(op.tmB, 0, sizeof(op.tmB));
+      YB_TRY(make_tiled_map(&op.tmB[bn_index(FUSE_COUT)], op.d_wt, op.cout_pad, K, K, FUSE_COUT, FUSE_CMID));
+      cuuint64_t dims[4] = {(cuuint64_t)op.cout, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
+      cuuint64_t strides[3] = {(cuuint64_t)op.out.ld * 2, (cuuint64_t)op.Wo * op.out.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.out.ld * 2};
+      cuuint32_t box[4] = {32, (cuuint32_t)FUSE_TW, 2, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), dims, strides, box, es,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D output) failed (%d) for layer %d", (int)r, op.layer);
+      continue;
+    }
     if (op.kind != OP_CONV || op.path != PATH_TC) continue;
     const void* in_ptr = view_ptr(e, op.in);
     if (op.ksize == 1 && op.stride == 1) {
@@ -1165,7 +1262,7 @@ static int autotune(yb_engine* e, int n, int reps) {
   char line[512];
   for (size_t oi = 0; oi < e->ops.size(); ++oi) {
     Op& op = e->ops[oi];
-    if (op.kind != OP_CONV || op.path != PATH_TC) continue;
+    if (op.kind != OP_CONV || op.path != PATH_TC || op.skip) continue;
     const long long sig[12] = {op.cin, op.cout, op.ksize, op.stride, op.Ho, op.Wo, op.has_res, op.out_mode, op.out.f32 ? 1 : 0,
                                op.leaky, op.in.ld, op.out.ld};
     const Done* hit = nullptr;
@@ -1314,6 +1411,10 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   e->keep_all = ka && atoi(ka) != 0;
   const char* fu = getenv("YB_FUSE_UPSAMPLE");
   if (fu) e->fuse_upsample = atoi(fu) != 0;
+  const char* fs = getenv("YB_FUSE_STEM");
+  if (fs) e->fuse_stem = atoi(fs);
+  const char* fb = getenv("YB_FUSE_BLOCK");
+  if (fb) e->fuse_block = atoi(fb);
   const char* pp = getenv("YB_PIXEL_PAIRS");
   if (pp) e->pixel_pairs = atoi(pp);
   const char* pd = getenv("YB_PDL");
@@ -1330,6 +1431,7 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   int r = compile_plan(e);
   if (r == YB_OK) {
     auto go = [&]() -> int {
+      YB_TRY(set_kernel_attrs(e));
       YB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
       YB_CUDA(cudaMalloc(&e->arena, e->arena_bytes));
       YB_CUDA(cudaMemset(e->arena, 0, e->arena_bytes));
@@ -1522,7 +1624,8 @@ static int try_graph_forward(yb_engine* e, int n, int slot) {
   // reader of the input; irrelevant at the batch sizes graphs are used for)
   if (slot >= 0) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
   ++e->graph_replays;
-  e->fwd_launches = (int)e->ops.size();
+  e->fwd_launches = 0;
+  for (const Op& op : e->ops) if (!op.skip) ++e->fwd_launches;
   e->last_n = n;
   e->detected = false;
   return 1;
@@ -1546,7 +1649,7 @@ static int enqueue_ops(yb_engine* e, int n, int slot, cudaEvent_t* evs, int* n_e
     if (evs) YB_CUDA(cudaEventRecord(evs[k], e->stream));
     YB_TRY(run_op(e, op, n));
     if (slot >= 0 && k == e->last_input_reader) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
-    ++e->fwd_launches;
+    if (!op.skip) ++e->fwd_launches;
     ++k;
   }
   if (evs) { YB_CUDA(cudaEventRecord(evs[k], e->stream)); if (n_ev) *n_ev = k + 1; }
@@ -1937,7 +2040,11 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   if (stages) *stages = op.launched_stages;
   // a pixel-pair op multiplies twice the useful products (half of its packed weights are structural zeros)
   // (px_pair == 2: the 3 x 2 kernel over 64 channels holds the 3 x 3 x 32 useful products)
-  if (flops_per_image) *flops_per_image = op.kind == OP_CONV ? 2.0 * op.Ho * op.Wo * op.cout * op.ksize * op.ksize * op.cin / (op.px_pair ? 2.0 : 1.0) : 0.0;
+  auto conv_flops = [](const Op& o) { return 2.0 * o.Ho * o.Wo * o.cout * o.ksize * o.ksize * o.cin / (o.px_pair ? 2.0 : 1.0); };
+  if (flops_per_image) {
+    *flops_per_image = (op.kind == OP_CONV && !op.skip) ? conv_flops(op) : 0.0;
+    if (op.kind == OP_CONV && op.fuse_kind) *flops_per_image += conv_flops(e->ops[op.fuse_src]);     // both layers of a fused pair
+  }
   return YB_OK;
 }
 
