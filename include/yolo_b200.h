@@ -15,6 +15,17 @@
  *     compute entry point fails with YB_ERR_CUDA.
  *   - "host" pointers are ordinary (pageable or pinned) memory; "device" pointers are CUDA device
  *     memory on the engine's device (yb_mem says which).
+ *   - STREAM ORDER.  Every engine (and every yb_post) runs on a stream of its own (cudaStreamNonBlocking): its work is
+ *     NOT ordered against work the caller enqueues on other streams.  A YB_MEM_DEVICE input must be complete before
+ *     the call that reads it and must not be overwritten while the engine may still read it.  Either synchronise the
+ *     producing stream, or bracket the call: yb_engine_order_after(e, producer_stream) before yb_engine_forward, and
+ *     yb_engine_order_before(e, stream) before `stream` rewrites the buffer (same for yb_post_*).  A YB_MEM_HOST
+ *     input of yb_engine_forward is copied asynchronously: keep it alive and unmodified until the forward after
+ *     next has been issued, or until yb_engine_sync (two staging slots are in flight at most).
+ *   - thresholds are doubles, as the reference's Python floats are.  The score threshold is compared in float32
+ *     (numpy >= 2 casts the Python float to the float32 score's dtype: NEP 50 weak scalars), the IoU threshold in
+ *     float64 against the float64 IoU (net/base.py:203) -- or in float32 when every box attribute is float32 (yb_nms).
+ *     A NaN score never becomes a candidate (the reference would keep the row and then sort NaN keys: undefined order).
  */
 #ifndef YOLO_B200_H_
 #define YOLO_B200_H_
@@ -26,7 +37,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 1
+#define YB_ABI_VERSION 2
 #define YB_MAX_SRC 4
 #define YB_MAX_ANCHORS 16
 
@@ -152,11 +163,17 @@ int yb_engine_read_layer(yb_engine* e, int layer, float* host_out, size_t capaci
  * (score-descending) order (row stride is always max_per_image); counts[n] receives the number of kept
  * boxes per image, which may exceed max_per_image -- then only the first max_per_image were written.
  * Synchronises the engine's stream. */
-int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode,
+int yb_engine_detect(yb_engine* e, double threshold, double iou_threshold, int nms_mode,
                      yb_det* out, int* counts, int max_per_image);
 /* Same, but leaves the results on the device (for device-timed benches); returns after enqueueing. */
-int yb_engine_detect_async(yb_engine* e, float threshold, float iou_threshold, int nms_mode);
+int yb_engine_detect_async(yb_engine* e, double threshold, double iou_threshold, int nms_mode);
 int yb_engine_sync(yb_engine* e);
+/* Stream ordering against the caller's CUDA streams (cuda_stream: a cudaStream_t / CUstream handle, NULL = the legacy
+ * default stream).  order_after: the engine's stream waits for everything enqueued on cuda_stream so far (call it
+ * before yb_engine_forward when that stream produces a YB_MEM_DEVICE input).  order_before: cuda_stream waits until
+ * the engine has consumed the input of its last forward (call it before that stream overwrites the input buffer). */
+int yb_engine_order_after(yb_engine* e, void* cuda_stream);
+int yb_engine_order_before(yb_engine* e, void* cuda_stream);
 
 /* per-op timing of the last forward+detect, measured with CUDA events on the engine's stream:
  * fills up to cap entries of (plan layer index or -1, milliseconds); returns the number of ops in *n_ops */
@@ -207,7 +224,8 @@ int yb_engine_fetch_wait(yb_engine* e, int slot);
  * milliseconds per launched op (layer_idx = plan entry that op implements) over n_forwards forwards. */
 int yb_engine_profiling(yb_engine* e, int enable);
 int yb_engine_profile_read(yb_engine* e, int* layer_idx, float* ms_sum, int cap, int* n_ops, int* n_forwards);
-/* Describes launched op `op_index`: path 0 = tcgen05 conv, 1 = direct first conv, 2 = CUDA-core conv,
+/* Describes launched op `op_index`: path 0 = tcgen05 conv, 1 = direct first conv, 2 = CUDA-core conv, 3 = fused pair
+ * (this conv also computes the conv feeding it, whose own op reports 0 FLOPs and is never launched),
  * negative = non-conv kernel; tile shape; algorithmic FLOPs per image (2*MAC). */
 int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn_tile, int* bk, int* stages,
                       double* flops_per_image);
@@ -232,12 +250,16 @@ void yb_post_destroy(yb_post* p);
  * Runs decode -> sort -> NMS on the device; out/counts as in yb_engine_detect (may be NULL to
  * leave results on the device).  cand_counts (optional, [n]) receives the number of candidates that
  * passed the threshold before NMS. */
-int yb_post_run(yb_post* p, const float* head, int mem, int n, float threshold, float iou_threshold,
+int yb_post_run(yb_post* p, const float* head, int mem, int n, double threshold, double iou_threshold,
                 int nms_mode, yb_det* out, int* counts, int max_per_image, int* cand_counts);
 /* decode only: candidates of image i in undefined order (sort by row to compare), host output. */
-int yb_post_decode(yb_post* p, const float* head, int mem, int n, float threshold,
+int yb_post_decode(yb_post* p, const float* head, int mem, int n, double threshold,
                    yb_det* out, int* counts, int max_per_image);
 int yb_post_sync(yb_post* p);
+/* as yb_engine_order_after / yb_engine_order_before, for a YB_MEM_DEVICE head tensor (order_before: cuda_stream waits
+ * for everything the context has enqueued so far) */
+int yb_post_order_after(yb_post* p, void* cuda_stream);
+int yb_post_order_before(yb_post* p, void* cuda_stream);
 /* device time of the last yb_post_run split by stage, milliseconds (decode, sort+nms) */
 int yb_post_last_ms(yb_post* p, float* decode_ms, float* nms_ms);
 

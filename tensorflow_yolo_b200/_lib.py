@@ -56,10 +56,14 @@ _SIGNATURES = {
     "yb_engine_output_shape": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_int), _P(ctypes.c_int)]),
     "yb_engine_read_layer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                             _P(ctypes.c_int * 3)]),
-    "yb_engine_detect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+    "yb_engine_detect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
-    "yb_engine_detect_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_int]),
+    "yb_engine_detect_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
     "yb_engine_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "yb_engine_order_after": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_engine_order_before": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_post_order_after": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "yb_post_order_before": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "yb_engine_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int)]),
     "yb_engine_set_conv_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -85,10 +89,10 @@ _SIGNATURES = {
     "yb_post_create": (ctypes.c_int, [_P(yb_scale), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _P(ctypes.c_void_p)]),
     "yb_post_destroy": (None, [ctypes.c_void_p]),
-    "yb_post_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
-                                   ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+    "yb_post_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                    ctypes.c_void_p]),
-    "yb_post_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+    "yb_post_decode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "yb_post_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "yb_post_last_ms": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_float), _P(ctypes.c_float)]),
@@ -114,7 +118,7 @@ def lib():
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(handle, name)     # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = restype, argtypes
-    if handle.yb_abi_version() != 1:
+    if handle.yb_abi_version() != 2:
         raise ImportError("libyolo_b200.so ABI version mismatch")
     _lib = handle
     return _lib

@@ -323,7 +323,7 @@ struct Op {
   __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
   alignas(64) CUtensorMap tmA, tmOut, tmRes;
-  alignas(64) CUtensorMap tmOut4;           // fused ops: output as (C, W, H, N), box 32 x 16 x 2 x 1
+  alignas(64) CUtensorMap tmOut4, tmRes4;   // fused ops: output / residual as (C, W, H, N), box 64 x 16 x 2 x 1
   alignas(64) CUtensorMap tmB[4];           // weight maps with box rows 32, 64, 128, 256 (128 doubles as the pair half)
   bool tma_epi = false;
   // generic
@@ -526,6 +526,7 @@ struct yb_engine {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_input_free[2] = {nullptr, nullptr};
   int stage_toggle = 0;
   int last_input_reader = 0;                 // index of the last op that reads the network input
+  cudaEvent_t ev_input_read = nullptr;       // recorded behind the last reader of the network input (yb_engine_order_before)
   cudaEvent_t marks[8] = {nullptr};
   cudaEvent_t ev_fetch[2] = {nullptr, nullptr};
   bool prof_on = false;
@@ -711,6 +712,7 @@ static int launch_fused(yb_engine* e, Op& op, int n) {
   a.scale1 = pp.d_scale; a.shift1 = pp.d_shift; a.scale2 = op.d_scale; a.shift2 = op.d_shift;
   a.leaky1 = pp.leaky; a.leaky2 = op.leaky;
   a.tiles_h = op.Ho / FUSE_TH; a.tiles_w = op.Wo / FUSE_TW; a.n_tiles = n * a.tiles_h * a.tiles_w;
+  a.dbg = e->dbg_counters;
   const int grid = std::min(a.n_tiles, e->num_sms);
   const CUtensorMap& tmB = op.tmB[bn_index(FUSE_COUT)];
   if (op.fuse_kind == FUSE_STEM) {
@@ -719,7 +721,7 @@ static int launch_fused(yb_engine* e, Op& op, int n) {
     else stem_fused_kernel<false><<<grid, FUSE_THREADS, FUSE_SMEM_STEM, e->stream>>>(tmB, op.tmOut4, a);
   } else {
     a.w1 = pp.d_wt;
-    block_fused_kernel<<<grid, FUSE_THREADS, FUSE_SMEM_BLOCK, e->stream>>>(tmB, op.tmOut4, a);
+    block_fused_kernel<<<grid, FUSE_THREADS, FUSE_SMEM_BLOCK, e->stream>>>(tmB, op.tmOut4, op.tmRes4, a);
   }
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -1146,12 +1148,20 @@ static int build_tensor_maps(yb_engine* e) {
       YB_TRY(make_tiled_map(&op.tmB[bn_index(FUSE_COUT)], op.d_wt, op.cout_pad, K, K, FUSE_COUT, FUSE_CMID));
       cuuint64_t dims[4] = {(cuuint64_t)op.cout, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
       cuuint64_t strides[3] = {(cuuint64_t)op.out.ld * 2, (cuuint64_t)op.Wo * op.out.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.out.ld * 2};
-      cuuint32_t box[4] = {32, (cuuint32_t)FUSE_TW, 2, 1};
+      cuuint32_t box[4] = {(cuuint32_t)FUSE_COUT, (cuuint32_t)FUSE_TW, 2, 1};      // 128-byte rows: SWIZZLE_128B
       cuuint32_t es[4] = {1, 1, 1, 1};
       CUresult r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), dims, strides, box, es,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D output) failed (%d) for layer %d", (int)r, op.layer);
+      memset(&op.tmRes4, 0, sizeof(op.tmRes4));
+      if (op.fuse_kind == FUSE_BLOCK) {       // the residual is the producer's input tensor
+        cuuint64_t rstrides[3] = {(cuuint64_t)op.in2.ld * 2, (cuuint64_t)op.Wo * op.in2.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.in2.ld * 2};
+        r = g_encode_tiled(&op.tmRes4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.in2), dims, rstrides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D residual) failed (%d) for layer %d", (int)r, op.layer);
+      }
       continue;
     }
     if (op.kind != OP_CONV || op.path != PATH_TC) continue;
@@ -1443,6 +1453,7 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
         YB_CUDA(cudaEventCreateWithFlags(&e->ev_fetch[i], cudaEventDisableTiming));
       }
       for (int i = 0; i < 8; ++i) YB_CUDA(cudaEventCreate(&e->marks[i]));
+      YB_CUDA(cudaEventCreateWithFlags(&e->ev_input_read, cudaEventDisableTiming));
       e->last_input_reader = 0;
       for (size_t i = 0; i < e->ops.size(); ++i)
         if (e->ops[i].in.buf == -2 || e->ops[i].in2.buf == -2) e->last_input_reader = (int)i;
@@ -1478,6 +1489,7 @@ void yb_engine_destroy(yb_engine* e) {
     if (e->ev_fetch[i]) cudaEventDestroy(e->ev_fetch[i]);
   }
   for (int i = 0; i < 8; ++i) if (e->marks[i]) cudaEventDestroy(e->marks[i]);
+  if (e->ev_input_read) cudaEventDestroy(e->ev_input_read);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1623,6 +1635,7 @@ static int try_graph_forward(yb_engine* e, int n, int slot) {
   // the staging buffer is free again once the whole graph has run (coarser than the eager path's event after the last
   // reader of the input; irrelevant at the batch sizes graphs are used for)
   if (slot >= 0) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
+  YB_CUDA(cudaEventRecord(e->ev_input_read, e->stream));
   ++e->graph_replays;
   e->fwd_launches = 0;
   for (const Op& op : e->ops) if (!op.skip) ++e->fwd_launches;
@@ -1648,7 +1661,10 @@ static int enqueue_ops(yb_engine* e, int n, int slot, cudaEvent_t* evs, int* n_e
   for (Op& op : e->ops) {
     if (evs) YB_CUDA(cudaEventRecord(evs[k], e->stream));
     YB_TRY(run_op(e, op, n));
-    if (slot >= 0 && k == e->last_input_reader) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
+    if (k == e->last_input_reader) {
+      if (slot >= 0) YB_CUDA(cudaEventRecord(e->ev_input_free[slot], e->stream));
+      YB_CUDA(cudaEventRecord(e->ev_input_read, e->stream));
+    }
     if (!op.skip) ++e->fwd_launches;
     ++k;
   }
@@ -1798,16 +1814,17 @@ int yb_engine_read_layer(yb_engine* e, int layer, float* host_out, size_t capaci
   return YB_OK;
 }
 
-int yb_engine_detect_async(yb_engine* e, float threshold, float iou_threshold, int nms_mode) {
+int yb_engine_detect_async(yb_engine* e, double threshold, double iou_threshold, int nms_mode) {
   if (!e) return fail(YB_ERR_INVALID, "yb_engine_detect: engine is NULL");
   if (e->last_n <= 0) return fail(YB_ERR_STATE, "yb_engine_detect before yb_engine_forward");
   if (nms_mode != YB_NMS_REFERENCE && nms_mode != YB_NMS_PER_CLASS) return fail(YB_ERR_INVALID, "unknown nms mode %d", nms_mode);
   YB_TRY(set_device(e->device));
   ScaleDesc sc[POST_MAX_SCALES];
   engine_scales(e, sc);
-  YB_TRY(e->post.decode(e->stream, sc, e->last_n, threshold));
-  // the reference compares the float64 IoU with the Python float threshold (net/base.py:203)
-  YB_TRY(e->post.nms(e->stream, e->last_n, (double)iou_threshold, nms_mode));
+  // score: numpy >= 2 compares the float32 score with the Python float cast to float32 (NEP 50), net/v3.py:121
+  YB_TRY(e->post.decode(e->stream, sc, e->last_n, (float)threshold));
+  // IoU: float64 against the Python float itself (net/base.py:203)
+  YB_TRY(e->post.nms(e->stream, e->last_n, iou_threshold, nms_mode));
   e->det_launches = 2;
   e->detected = true;
   return YB_OK;
@@ -1824,10 +1841,33 @@ static int copy_dets(PostCtx& post, cudaStream_t st, int n, yb_det* out, int* co
   return YB_OK;
 }
 
-int yb_engine_detect(yb_engine* e, float threshold, float iou_threshold, int nms_mode, yb_det* out, int* counts, int max_per_image) {
+int yb_engine_detect(yb_engine* e, double threshold, double iou_threshold, int nms_mode, yb_det* out, int* counts, int max_per_image) {
   if (!out || !counts) return fail(YB_ERR_INVALID, "yb_engine_detect: output buffers are NULL");
   YB_TRY(yb_engine_detect_async(e, threshold, iou_threshold, nms_mode));
   return copy_dets(e->post, e->stream, e->last_n, out, counts, max_per_image, &e->det_launches);
+}
+
+// ---- stream ordering against the caller's streams (include/yolo_b200.h, "STREAM ORDER") ----
+static int order_streams(cudaStream_t first, cudaStream_t then) {
+  cudaEvent_t ev = nullptr;
+  YB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t r = cudaEventRecord(ev, first);
+  if (r == cudaSuccess) r = cudaStreamWaitEvent(then, ev, 0);
+  cudaEventDestroy(ev);          // released once the recorded work has completed
+  if (r != cudaSuccess) { cudaGetLastError(); return fail(YB_ERR_CUDA, "stream ordering failed: %s", cudaGetErrorString(r)); }
+  return YB_OK;
+}
+int yb_engine_order_after(yb_engine* e, void* cuda_stream) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  YB_TRY(set_device(e->device));
+  return order_streams(static_cast<cudaStream_t>(cuda_stream), e->stream);
+}
+int yb_engine_order_before(yb_engine* e, void* cuda_stream) {
+  if (!e) return fail(YB_ERR_INVALID, "engine is NULL");
+  YB_TRY(set_device(e->device));
+  if (!e->ev_input_read) return YB_OK;                   // no forward yet
+  YB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(cuda_stream), e->ev_input_read, 0));
+  return YB_OK;
 }
 
 int yb_engine_sync(yb_engine* e) {
@@ -2112,7 +2152,7 @@ void yb_post_destroy(yb_post* p) {
   delete p;
 }
 
-static int post_stage_and_decode(yb_post* p, const float* head, int mem, int n, float threshold) {
+static int post_stage_and_decode(yb_post* p, const float* head, int mem, int n, double threshold) {
   if (!p || !head) return fail(YB_ERR_INVALID, "yb_post: bad argument");
   if (n <= 0 || n > p->ctx.max_batch) return fail(YB_ERR_INVALID, "batch %d outside [1,%d]", n, p->ctx.max_batch);
   YB_TRY(set_device(p->device));
@@ -2135,16 +2175,16 @@ static int post_stage_and_decode(yb_post* p, const float* head, int mem, int n, 
     sc[i].cell_stride = sc[i].na * p->ctx.box_len;
   }
   YB_CUDA(cudaEventRecord(p->ctx.ev[0], p->stream));
-  YB_TRY(p->ctx.decode(p->stream, sc, n, threshold));
+  YB_TRY(p->ctx.decode(p->stream, sc, n, (float)threshold));      // float32 compare: NEP 50 (see yb_engine_detect_async)
   YB_CUDA(cudaEventRecord(p->ctx.ev[1], p->stream));
   return YB_OK;
 }
 
-int yb_post_run(yb_post* p, const float* head, int mem, int n, float threshold, float iou_threshold, int nms_mode,
+int yb_post_run(yb_post* p, const float* head, int mem, int n, double threshold, double iou_threshold, int nms_mode,
                 yb_det* out, int* counts, int max_per_image, int* cand_counts) {
   if (nms_mode != YB_NMS_REFERENCE && nms_mode != YB_NMS_PER_CLASS) return fail(YB_ERR_INVALID, "unknown nms mode %d", nms_mode);
   YB_TRY(post_stage_and_decode(p, head, mem, n, threshold));
-  YB_TRY(p->ctx.nms(p->stream, n, (double)iou_threshold, nms_mode));
+  YB_TRY(p->ctx.nms(p->stream, n, iou_threshold, nms_mode));
   YB_CUDA(cudaEventRecord(p->ctx.ev[2], p->stream));
   p->timed = true;
   if (out && counts) {
@@ -2170,12 +2210,23 @@ __global__ void list_candidates_kernel(int rows, const float* prob, int* order, 
   }
 }
 
-int yb_post_decode(yb_post* p, const float* head, int mem, int n, float threshold, yb_det* out, int* counts, int max_per_image) {
+int yb_post_decode(yb_post* p, const float* head, int mem, int n, double threshold, yb_det* out, int* counts, int max_per_image) {
   if (!out || !counts) return fail(YB_ERR_INVALID, "yb_post_decode: output buffers are NULL");
   YB_TRY(post_stage_and_decode(p, head, mem, n, threshold));
   list_candidates_kernel<<<n, 32, 0, p->stream>>>(p->ctx.rows, p->ctx.prob, p->ctx.order, p->ctx.n_keep);
   YB_CUDA(cudaGetLastError());
   return copy_dets(p->ctx, p->stream, n, out, counts, max_per_image, nullptr);
+}
+
+int yb_post_order_after(yb_post* p, void* cuda_stream) {
+  if (!p) return fail(YB_ERR_INVALID, "post context is NULL");
+  YB_TRY(set_device(p->device));
+  return order_streams(static_cast<cudaStream_t>(cuda_stream), p->stream);
+}
+int yb_post_order_before(yb_post* p, void* cuda_stream) {
+  if (!p) return fail(YB_ERR_INVALID, "post context is NULL");
+  YB_TRY(set_device(p->device));
+  return order_streams(p->stream, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int yb_post_sync(yb_post* p) {

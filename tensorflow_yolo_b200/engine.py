@@ -26,6 +26,18 @@ def _buffer(arr, np_dtypes):
     raise TypeError("expected a numpy array or a torch tensor")
 
 
+def _producer_stream(arr):
+    """CUDA stream handle (int) the caller's framework is currently enqueueing on for a device tensor, or None.
+    Only torch is recognised (through the already-imported module: this package never imports it itself)."""
+    if not (hasattr(arr, "is_cuda") and arr.is_cuda):
+        return None
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is None:
+        return None
+    return int(torch.cuda.current_stream(arr.device).cuda_stream)
+
+
 def _raw_image_args(images):
     keep = []
     n = len(images)
@@ -94,15 +106,22 @@ class Engine(object):
         shape = tuple(images.shape)
         if len(shape) != 4 or shape[1:] != self.input_shape:
             raise ValueError("expected images of shape [n,{},{},{}], got {}".format(*(self.input_shape + (shape,))))
-        self._keep = keep
+        # host inputs are copied asynchronously from the caller's memory: up to two H2D copies are in flight (two staging
+        # slots), so the last three inputs are kept alive here; device inputs are ordered against the producing stream
+        self._keep = (getattr(self, "_keep", ()) + (keep,))[-3:]
+        ps = _producer_stream(images)
+        if ps is not None:
+            _lib.check(_lib.lib().yb_engine_order_after(self._h, ps))
         _lib.check(_lib.lib().yb_engine_forward(self._h, ptr, _lib.YB_F32 if dt == np.float32 else _lib.YB_U8, mem, shape[0]))
+        if ps is not None:      # later writes to the tensor on that stream wait until the first conv has read it
+            _lib.check(_lib.lib().yb_engine_order_before(self._h, ps))
         self.last_n = shape[0]
 
     def forward_raw(self, images):
         """images: list of uint8 BGR arrays [h, w, 3] as cv2.imread returns them (any sizes).  Resize (cv2 INTER_LINEAR,
         bit-exact), BGR->RGB and /255 run on the device, then the conv stack.  Asynchronous."""
         ptrs, hs, ws, strides, keep = _raw_image_args(images)
-        self._keep = keep
+        self._keep = (getattr(self, "_keep", ()) + (keep,))[-3:]
         _lib.check(_lib.lib().yb_engine_forward_raw(self._h, ptrs, hs, ws, strides, len(images)))
         self.last_n = len(images)
 
@@ -297,8 +316,14 @@ class PostProcessor(object):
 
     def run(self, head, threshold, iou_threshold, nms_mode=YB_NMS_REFERENCE, max_per_image=None, fetch=True):
         ptr, mem, n, keep = self._head(head)
+        ps = _producer_stream(head)
+        if ps is not None:
+            _lib.check(_lib.lib().yb_post_order_after(self._h, ps))
         if not fetch:
             _lib.check(_lib.lib().yb_post_run(self._h, ptr, mem, n, threshold, iou_threshold, nms_mode, None, None, 0, None))
+            if ps is not None:
+                _lib.check(_lib.lib().yb_post_order_before(self._h, ps))
+            self._keep = keep
             return None
         cap = int(max_per_image or self.rows)
         dets = np.zeros((n, cap), dtype=DET_DTYPE)

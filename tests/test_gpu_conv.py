@@ -252,7 +252,7 @@ def test_cuda_graph_forward_is_bit_identical_and_replayed():
         assert np.array_equal(eng.read_output(), y8), it
     assert eng.graph_replays() >= 12
     fwd, _ = eng.launch_count()
-    assert fwd == 75
+    assert fwd == 73          # 75 convs; the first conv and the 1x1 of the first block run inside their consumers (conv_fused.cuh)
     # a configuration change drops the captured graphs; results stay the same
     n_before = eng.graph_replays()
     eng.set_option("pdl", 0)

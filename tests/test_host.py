@@ -137,7 +137,7 @@ def test_cabi_exports_every_declared_symbol(lib_built):
     handle = ctypes.CDLL(lib_built)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().yb_abi_version() == 1
+    assert _lib.lib().yb_abi_version() == 2
     assert ctypes.sizeof(_lib.yb_det) == 40 and np.dtype(_lib.DET_DTYPE).itemsize == 40
     assert ctypes.sizeof(P.yb_layer) == 4 * (7 + 4 + 1 + 32)
 
