@@ -5,10 +5,14 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
   python bench.py --impl reference ...                                (CPU arm: the oracle port on host cores)
 
-A "step" is one pass of the hot path over one batch per GPU: yb_engine_forward (75 convs) +
+A "step" is one pass of the hot path over one batch per GPU: yb_engine_forward (75 convs in 73 launches) +
 yb_engine_detect_async (decode, sort, NMS).  The batch is sharded across ranks with no collective
-(detections are per image), so scaling is weak: 128 images per GPU per step.  `value` is measured with the
+(detections are per image).  The headline line is weak scaling: 128 images per GPU per step (--scaling strong keeps
+the global batch at --batch and gives every rank its shard_bounds share).  `value` is measured with the
 inputs already resident in HBM, by CUDA events recorded on the engine's own stream, max over ranks.
+Besides the headline the line carries `sustained` (the same step over a >= 2 s loop, i.e. under the power cap) and
+`extra`: BASELINE config 3 split strongly over the ranks (128 / N images per GPU), config 4 (YOLOv3-608, 64 per GPU)
+and config 5 (decode + NMS alone on [1024 / N, 10647, 85] dense heads) -- see SURVEY 8(d)/(e).
 `e2e` is the same metric through the host-buffer API: every step copies its uint8 NHWC images from pinned host
 memory and reads the kept detections back (copies pipelined against compute on a separate stream).
 torch is used only for pinned/device buffers, the rank barrier and the max-reduction of the timings.
@@ -105,6 +109,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+V2_HEAD = {"head_std": 4.0, "obj_bias": -6.0}       # synthetic v2 heads: sharp class softmax, ~tens of kept boxes per image
+
+
 V2_ANCHORS = {"v2voc": [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071],
               "v2coco": [0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828]}
 
@@ -125,7 +132,10 @@ def build_network(size, net_name="v3"):
     else:
         net = pv2.create_full_network(np.reshape(V2_ANCHORS[net_name], [-1, 2]), names, False, input_shape=shape)
     state = net[0]._yb_state
-    stream = synth.weight_stream(state.graph.specs, seed=2, num_classes=nc, obj_bias=OBJ_BIAS if net_name == "v3" else 1.0)
+    if net_name == "v3":
+        stream = synth.weight_stream(state.graph.specs, seed=2, num_classes=nc, obj_bias=OBJ_BIAS)
+    else:
+        stream = synth.weight_stream(state.graph.specs, seed=2, num_classes=nc, **V2_HEAD)
     return net, state, stream, shape
 
 
@@ -184,6 +194,133 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
+def traffic_key(ks, st, cin, co, ho, wo, bn, bk, pair, batch):
+    return "{}x{}s{}_{}->{}@{}x{}_BN{}_BK{}_PAIR{}_b{}".format(ks, ks, st, cin, co, ho, wo, bn, bk, int(pair), batch)
+
+
+def v3_scales(size):
+    """(h, w, anchors in grid units) per scale in detection order 13, 26, 52 (net/v3.py:11,53,69,85)."""
+    anchors = np.reshape(V3_ANCHORS, [-1, 2]).astype(np.float64)
+    out = []
+    for i, stride in enumerate((32, 16, 8)):
+        a = anchors[[6, 7, 8]] if i == 0 else anchors[[3, 4, 5]] if i == 1 else anchors[[0, 1, 2]]
+        out.append((size // stride, size // stride, [(aw / stride, ah / stride) for aw, ah in a]))
+    return out
+
+
+def time_steps(eng, x_dev, steps, barrier, max_over_ranks, warmup=3):
+    """Device milliseconds per step (forward + decode + NMS, inputs resident), max over ranks."""
+    for _ in range(warmup):
+        eng.forward(x_dev); eng.detect_async(THRESHOLD, IOU_THRESHOLD)
+    eng.sync()
+    barrier()
+    eng.mark(6)
+    for _ in range(steps):
+        eng.forward(x_dev); eng.detect_async(THRESHOLD, IOU_THRESHOLD)
+    eng.mark(7)
+    eng.sync()
+    barrier()
+    return max_over_ranks(eng.elapsed_ms(6, 7)) / steps
+
+
+def run_extras(args, world, rank, local, barrier, max_over_ranks, eng_main):
+    """The configurations of BASELINE.json that the headline line does not show, each measured like `value`
+    (inputs resident in HBM, CUDA events on the engine's stream, max over ranks, whole-job images/s):
+      strong  config 3 with the global batch fixed at 128: 128 / N images per GPU
+      config4 YOLOv3-608, 64 images per GPU (512 over 8 GPUs)
+      config5 decode + NMS alone on dense heads [1024 / N per GPU, 10647, 85], score threshold 0.001"""
+    import torch
+    from tensorflow_yolo_b200 import engine as yb, plan as yplan, sharding
+    peaks = load_peaks()
+    steps = args.extra_steps
+    out = {}
+    g = torch.Generator(device="cuda"); g.manual_seed(11 + rank)
+    # ---- config 3, strong split ----
+    lo, hi = sharding.shard_bounds(128, world, rank)
+    nb = hi - lo
+    if world == 1:
+        out["config3_strong"] = {"global_batch": 128, "batch_per_gpu": 128, "note": "identical to the headline at N = 1"}
+    elif nb >= 1:
+        x = torch.rand((nb, 416, 416, 3), device="cuda", dtype=torch.float32, generator=g)
+        eng_main.autotune(nb, reps=3)             # tile configurations for the smaller per-GPU batch
+        ms = time_steps(eng_main, x, max(steps, 20), barrier, max_over_ranks)
+        out["config3_strong"] = {"global_batch": 128, "batch_per_gpu": nb, "ms_per_step": ms, "value": 128 / (ms * 1e-3), "unit": "images/s",
+                                 "scaling": "strong", "graph_replays": eng_main.graph_replays()}
+        del x
+    # ---- config 4: 608 x 608, 64 images per GPU ----
+    try:
+        net, state, stream, shape = build_network(608, "v3")
+        eng4 = yb.Engine(state.plan(), shape, NUM_CLASSES, yb.YB_DECODE_V3, max_batch=64, device=local)
+        eng4.load_weights(stream)
+        eng4.autotune(64, reps=2)
+        x = torch.rand((64,) + shape, device="cuda", dtype=torch.float32, generator=g)
+        ms = time_steps(eng4, x, steps, barrier, max_over_ranks)
+        fl = yplan.conv_flops(state.graph.specs)
+        v = world * 64 / (ms * 1e-3)
+        out["config4"] = {"workload": "YOLOv3-608 COCO-80, 64 images per GPU ({} in total)".format(64 * world), "ms_per_step": ms, "value": v,
+                          "unit": "images/s", "scaling": "weak", "conv_gflop_per_image": fl / 1e9,
+                          "whole_step_tflops_per_gpu": v / world * fl / 1e12,
+                          "frac_of_burst": v / world * fl / 1e12 / peaks["bf16_tflops"],
+                          "frac_of_sustained": v / world * fl / 1e12 / peaks["bf16_tflops_sustained"]}
+        eng4.close()
+        del x
+    except Exception as ex:       # an extra must never take the headline down with it
+        out["config4"] = {"error": str(ex)[:300]}
+    # ---- config 5: decode + NMS isolated, dense ----
+    try:
+        lo, hi = sharding.shard_bounds(1024, world, rank)
+        nb5, R, L = hi - lo, 10647, 85
+        post = yb.PostProcessor(v3_scales(416), 80, yb.YB_DECODE_V3, max_batch=nb5, device=local)
+        g5 = torch.Generator(device="cuda"); g5.manual_seed(rank)
+        head = torch.randn((nb5, R, L), device="cuda", dtype=torch.float32, generator=g5)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            barrier()
+            post.run(head, 0.001, IOU_THRESHOLD, fetch=False)
+            post.sync()
+            d, n = post.last_ms()
+            if best is None or d + n < best[0] + best[1]:
+                best = (d, n)
+        d_ms, n_ms = max_over_ranks(best[0]), max_over_ranks(best[1])
+        head_bytes = nb5 * R * L * 4
+        pairs = nb5 * (R * (R - 1) // 2)
+        # ALU bound of a brute-force greedy NMS: one IoU decision is >= 13 fp32 lane operations (4 min/max, 2 subtractions, 2
+        # clamps, 1 product, 2 for the union, the threshold product and the compare); 148 SMs x 128 lanes at the maximum clock
+        lanes_per_s = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+        alu_pairs_peak = lanes_per_s / 13.0
+        out["config5"] = {
+            "workload": "decode + NMS on dense heads [{} per GPU, 10647, 85] float32, score threshold 0.001 (every row a candidate), "
+                        "IoU threshold 0.6".format(nb5),
+            "decode_ms": d_ms, "nms_ms": n_ms, "value": 1024 / ((d_ms + n_ms) * 1e-3), "unit": "images/s",
+            "roofline_decode": {"bound": "hbm", "achieved": head_bytes / (d_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": head_bytes / (d_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                "algorithmic_bytes_per_launch": head_bytes},
+            "roofline_nms": {"bound": "alu", "achieved": pairs / (n_ms * 1e-3) / 1e12, "peak": alu_pairs_peak / 1e12,
+                             "unit": "T IoU pairs/s (algorithmic: K(K-1)/2 per image)", "frac": pairs / (n_ms * 1e-3) / alu_pairs_peak,
+                             "note": "peak = fp32 lanes x max clock / 13 operations per brute-force pair test; the kernel prunes "
+                                     "pairs with sorted-key tables, so a fraction above 1 means fewer than K(K-1)/2 tests were executed"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            # the oracle's NMS (net/base.py:195-209 restated, oracle/postprocess.py) on ONE dense image, wall-clock capped
+            from oracle import postprocess
+            h1 = head[:1].cpu().numpy()
+            t0 = time.perf_counter()
+            geo = [(h, w, len(a), a) for h, w, a in v3_scales(416)]
+            cand = postprocess.decode_v3_image(h1[0], geo, 0.001)
+            t1 = time.perf_counter()
+            keep = postprocess.nms(cand, IOU_THRESHOLD)
+            t2 = time.perf_counter()
+            out["config5"]["cpu_baseline"] = {"value": 1.0 / (t2 - t0), "unit": "images/s", "cores": 1, "kind": "port",
+                                              "sample": "1 dense image (K = {} candidates, {} kept): numpy decode {:.2f} s + greedy NMS "
+                                                        "{:.2f} s".format(len(cand["row"]), len(keep), t1 - t0, t2 - t1)}
+        post.close()
+        del head
+    except Exception as ex:
+        out["config5"] = {"error": str(ex)[:300]}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -210,7 +347,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    B, K, W = args.batch, args.steps, args.warmup
+    from tensorflow_yolo_b200 import sharding
+    K, W = args.steps, args.warmup
+    if args.scaling == "strong":          # the global batch is fixed; rank r takes its contiguous share
+        lo, hi = sharding.shard_bounds(args.batch, world, rank)
+        B, global_batch = hi - lo, args.batch
+        if B < 1:
+            raise SystemExit("--scaling strong: global batch {} smaller than the number of ranks {}".format(args.batch, world))
+    else:
+        B, global_batch = args.batch, args.batch * world
     net, state, stream, shape = build_network(args.size, args.net)
     eng = yb.Engine(state.plan(), shape, net_classes(args.net), yb.YB_DECODE_V3 if args.net == "v3" else yb.YB_DECODE_V2,
                     max_batch=B, device=local)
@@ -254,7 +399,7 @@ def run_ours(args):
     eng.sync()
     barrier()
     ms = max_over_ranks(eng.elapsed_ms(0, 1))
-    value = world * B * K / (ms * 1e-3)
+    value = global_batch * K / (ms * 1e-3)
     # ---- timed region 2: end to end through host buffers (H2D of uint8 images + D2H of detections each step) ----
     def e2e_loop(steps):
         kept = 0
@@ -277,7 +422,7 @@ def run_ours(args):
     dt = time.perf_counter() - t0
     barrier()
     dt = max_over_ranks(dt)
-    e2e_value = world * B * K / dt
+    e2e_value = global_batch * K / dt
     # ---- K more device-resident steps with a CUDA event between launches: per-kernel times for the roofline.  (Run after
     # both timed regions, so that `value` and `e2e` are measured back to back in the same power state; kept out of
     # region 1 because an event between two launches serialises them, i.e. switches off the programmatic dependent
@@ -294,7 +439,25 @@ def run_ours(args):
     prof, n_fwd = eng.profile_read()
     eng.profiling(False)
 
+    # ---- sustained: the same device-resident step over a loop of >= args.sustain_seconds (the chip sits at its 1000 W
+    # cap after a few hundred milliseconds of load; the K-step region above is a semi-burst number) ----
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(K, int(np.ceil(args.sustain_seconds * 1e3 / (ms / K))))
+        barrier()
+        eng.mark(4)
+        for _ in range(n_sus):
+            step_device()
+        eng.mark(5)
+        eng.sync()
+        barrier()
+        ms_sus = max_over_ranks(eng.elapsed_ms(4, 5))
+        sustained = {"value": global_batch * n_sus / (ms_sus * 1e-3), "unit": "images/s", "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / n_sus}
     clocks = sampler.stop() if sampler else None
+    extra = None
+    if not args.no_extra and args.net == "v3" and args.size == 416 and args.scaling == "weak":
+        extra = run_extras(args, world, rank, local, barrier, max_over_ranks, eng)
 
     if rank != 0:
         if world > 1:
@@ -332,15 +495,23 @@ def run_ours(args):
     top_key, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
     achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
-    traffic = None
+    (ho, wo, co), ks, st, cin, bn, bk, pair = top_key
+    # DRAM traffic per launch of the dominant class: only from an ncu capture of exactly this class (shape, tile, batch);
+    # null otherwise -- never a number borrowed from another kernel
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    (ho, wo, co), ks, st, cin, bn, bk, pair = top_key
+            table = json.load(f).get("classes", {})
+        hit = table.get(traffic_key(ks, st, cin, co, ho, wo, bn, bk, pair, B))
+        if hit:
+            traffic, traffic_src = hit["dram_bytes_per_launch"], hit["source"]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": "{} bf16_tflops_sustained (kernel timed inside a long step)".format(peaks["source"]),
+        "traffic_source": traffic_src,
+        "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"], "frac_of_burst": achieved / peaks["bf16_tflops"],
+        "peak_source": "{} bf16_tflops_sustained (kernel timed inside a long step); burst peak {} TFLOP/s".format(
+            peaks["source"], peaks["bf16_tflops"]),
         "kernel": "conv_tc_persist_kernel<BN={},BK={},PAIR={}>: {}x{} s{} conv {}->{} @{}x{} (share of step {:.1%}, {} launches/step)".format(
             bn, bk, pair, ks, ks, st, cin, co, ho, wo, top["ms"] / (ms_prof * n_fwd / K if n_fwd else 1), top["launches"] // max(n_fwd, 1)),
         "timing": "CUDA events between launches on the engine's stream over K steps repeated right after the timed region "
@@ -367,18 +538,19 @@ def run_ours(args):
                          "decode/NMS; TensorFlow itself is not installable)".format(reps, args.cpu_images)}
     line = {
         "metric": metric_name(args), "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "{}: {} convs + decode + NMS, random-init darknet .weights".format(
                        workload_name(args), sum(1 for sp in state.graph.specs if sp.kind == yplan.KIND_CONV)),
-                   "batch_per_gpu": B, "global_batch": B * world, "threshold": THRESHOLD, "iou_threshold": IOU_THRESHOLD,
+                   "batch_per_gpu": B, "global_batch": global_batch, "threshold": THRESHOLD, "iou_threshold": IOU_THRESHOLD,
                    "parallelism": "batch sharded over {} GPU(s), no collective".format(world),
                    "l2": l2_note(B, shape, state),
-                   "kept_detections_per_image": kept / float(B * K)},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * B * shape[0] * shape[1] * 3,
-                "d2h_bytes_per_step": world * B * (cap * 40 + 4), "input": "uint8 NHWC in pinned host memory, scaled by 1/255 on the device",
+                   "kept_detections_per_image": kept / float(max(B * K, 1))},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": global_batch * shape[0] * shape[1] * 3,
+                "d2h_bytes_per_step": global_batch * (cap * 40 + 4), "input": "uint8 NHWC in pinned host memory, scaled by 1/255 on the device",
                 "timer": "host wall clock around the synchronised region, max over ranks"},
         "gpu_launches": world * K * (fwd_l + det_l), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "sustained": sustained, "extra": extra,
         "conv_gflop_per_image": flops_img / 1e9,
         "autotune": None if tune is None else {
             "layers_changed": sum(1 for o in tune["ops"] if o["chosen"]["ms"] < o["default_ms"] * 0.985),
@@ -400,7 +572,12 @@ def main():
     ap.add_argument("--net", default="v3", choices=["v3", "v2voc", "v2coco"],
                     help="network: v3 (headline, BASELINE configs 3/4) or YOLOv2 VOC/COCO (configs 2/1)")
     ap.add_argument("--max-per-image", type=int, default=256)
-    ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline pass")
+    ap.add_argument("--cpu-images", type=int, default=8, help="images per CPU-baseline pass")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU; strong: --batch images in total, sharded over the ranks")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra sustained loop (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (strong split, config 4, config 5)")
+    ap.add_argument("--extra-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="wall-clock budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default=None, help="write the per-op CUDA-event table of the timed region (JSON)")

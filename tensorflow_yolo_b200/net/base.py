@@ -12,6 +12,7 @@ import numpy as np
 from .. import _lib
 from .. import engine as _engine
 from .. import plan as _plan
+from .. import sharding as _sharding
 
 COLORS = [(0, 0, 255), (0, 255, 0), (255, 0, 0), (0, 255, 255), (255, 255, 0), (255, 0, 255)]
 
@@ -52,10 +53,20 @@ class NetworkState(object):
         self.num_classes = num_classes
         self.anchors_v2 = anchors_v2
         self.input_shape = tuple(input_shape)
-        self.engine = None
-        self.max_batch = 0
-        self.device = int(os.environ.get("YB_DEVICE", "0"))
+        self.engines = []                # one per device in use, engines[i] on devices[i]
+        self.max_batch = 0               # images per call over all devices
+        self.devices = _sharding.visible_devices()
+        self.pool = None
         self.pending_stream = None
+
+    @property
+    def engine(self):
+        """The engine on the first device (the reference-protocol path, Session.run, uses only this one)."""
+        return self.engines[0] if self.engines else None
+
+    @property
+    def device(self):
+        return self.devices[0]
 
     def plan(self):
         specs = list(self.graph.specs)
@@ -69,24 +80,57 @@ class NetworkState(object):
         return specs
 
     def ensure_engine(self, batch):
-        if self.engine is not None and batch <= self.max_batch:
-            return self.engine
-        if self.engine is not None:
-            self.engine.close()
+        """Engines for calls of up to `batch` images: the batch is cut into contiguous shards, one per device
+        (sharding.shard_bounds), so every engine is sized for ceil(batch / devices) images.  Returns the first engine."""
+        if self.engines and batch <= self.max_batch:
+            return self.engines[0]
+        self.close_engines()
         mode = _engine.YB_DECODE_V2 if self.version == "v2" else _engine.YB_DECODE_V3
         self.max_batch = max(int(batch), int(os.environ.get("YB_MAX_BATCH", "1")))
-        self.engine = _engine.Engine(self.plan(), self.input_shape, self.num_classes, mode,
-                                     max_batch=self.max_batch, device=self.device)
+        n_dev = max(1, min(len(self.devices), self.max_batch))
+        per_device = -(-self.max_batch // n_dev)
+        self.pool = _sharding.DevicePool(n_dev)
+
+        def create(slot):          # on the device's own worker thread: the CUDA work of all devices overlaps
+            eng = _engine.Engine(self.plan(), self.input_shape, self.num_classes, mode, max_batch=per_device,
+                                 device=self.devices[slot])
+            if self.pending_stream is not None:
+                eng.load_weights(self.pending_stream)
+            return eng
+        self.engines = self.pool.each(create)
         if self.pending_stream is not None:
-            self.engine.load_weights(self.pending_stream)
             self.tune()
-        return self.engine
+        return self.engines[0]
+
+    def close_engines(self):
+        for eng in self.engines:
+            eng.close()
+        self.engines = []
+        if self.pool is not None:
+            self.pool.close()
+            self.pool = None
+
+    def load_stream(self, stream):
+        self.pending_stream = stream
+        if self.engines:
+            self.pool.each(lambda slot: self.engines[slot].load_weights(stream))
+            self.tune()
 
     def tune(self):
         """Per-layer launch configurations measured on the device for this engine's batch size (about a second, once
         per engine; results are bit-identical with or without it).  YB_AUTOTUNE=0 keeps the heuristic."""
-        if self.engine is not None and os.environ.get("YB_AUTOTUNE", "1") != "0":
-            self.engine.autotune(self.max_batch, reps=3)
+        if self.engines and os.environ.get("YB_AUTOTUNE", "1") != "0":
+            self.pool.each(lambda slot: self.engines[slot].autotune(self.engines[slot].max_batch, reps=3))
+
+    def detect(self, items, forward, threshold, iou_threshold):
+        """forward(engine, shard) + detect on every device's shard of `items`; per-item results in input order."""
+        self.ensure_engine(len(items))
+
+        def work(slot, shard):
+            eng = self.engines[slot]
+            forward(eng, shard)
+            return eng.detect(threshold, iou_threshold)
+        return self.pool.run(work, items)
 
 
 def state_of(layers):
@@ -103,10 +147,7 @@ class _AssignWeights(object):
         self.state, self.stream, self.read = state, stream, read
 
     def run(self):
-        self.state.pending_stream = self.stream
-        if self.state.engine is not None:
-            self.state.engine.load_weights(self.stream)
-            self.state.tune()
+        self.state.load_stream(self.stream)
 
 
 def load_weights(layers, weights):
@@ -326,7 +367,7 @@ def non_maximum_suppression(boxes, iou_threshold):
         return []
     get = lambda name: np.asarray([getattr(b, name) for b in boxes])
     keep = _engine.nms(get("x"), get("y"), get("w"), get("h"), get("prob").astype(np.float32), iou_threshold,
-                       device=int(os.environ.get("YB_DEVICE", "0")))
+                       device=_sharding.visible_devices()[0])
     return [boxes[i] for i in keep]
 
 

@@ -17,18 +17,18 @@ class Yolo(object):
 
     def detect_batch(self, net, x_batch, threshold, iou_threshold):
         """Fast path used by test(): forward + decode + NMS entirely on the GPU; only the kept boxes come back
-        (the reference's sess.run + find_bounding_boxes pair, net/yolo.py:83-86, without the D2H of net_out)."""
+        (the reference's sess.run + find_bounding_boxes pair, net/yolo.py:83-86, without the D2H of net_out).
+        The batch is cut into contiguous shards over every visible GPU (YB_DEVICES restricts them), one engine and
+        one host thread per device; the per-image results come back in input order."""
         state = base.state_of(net)
-        eng = state.ensure_engine(len(x_batch))
-        eng.forward(np.asarray(x_batch))
-        return [base.boxes_from_dets(d) for d in eng.detect(threshold, iou_threshold)]
+        dets = state.detect(np.asarray(x_batch), lambda eng, shard: eng.forward(shard), threshold, iou_threshold)
+        return [base.boxes_from_dets(d) for d in dets]
 
     def detect_batch_raw(self, net, raw_images, threshold, iou_threshold):
         """detect_batch on decoded BGR images: preprocessing (net/base.py:115-155) runs on the GPU as well."""
         state = base.state_of(net)
-        eng = state.ensure_engine(len(raw_images))
-        eng.forward_raw(raw_images)
-        return [base.boxes_from_dets(d) for d in eng.detect(threshold, iou_threshold)]
+        dets = state.detect(list(raw_images), lambda eng, shard: eng.forward_raw(shard), threshold, iou_threshold)
+        return [base.boxes_from_dets(d) for d in dets]
 
     def test(self, params):
         image_dir = params["image_dir"]

@@ -51,3 +51,32 @@ def test_two_ranks_gloo(tmp_path):
     assert a[:-1, 0].tolist() == [0.0, 4.0, 8.0, 12.0, 16.0, 20.0, 24.0]
     assert a[:-1, 1].tolist() == [0, 0, 0, 0, 1, 1, 1]                # contiguous shards: 4 + 3
     assert a[-1, 0] == 11.0                                           # max over ranks of (10 + rank)
+
+
+def test_device_pool_keeps_input_order_and_balances():
+    """The in-process driver (one host thread per GPU, sharding.DevicePool): contiguous shards, input order kept."""
+    import threading
+    pool = sharding.DevicePool(3)
+    seen = {}
+
+    def work(slot, shard):
+        seen.setdefault(slot, []).append((threading.get_ident(), list(shard)))
+        return [v * v for v in shard]
+    for n in (0, 1, 2, 3, 7, 10):
+        items = list(range(n))
+        assert pool.run(work, items) == [v * v for v in items]
+    sizes = [len(s) for _, s in (seen[0][-1], seen[1][-1], seen[2][-1])]
+    assert sizes == [4, 3, 3]                                     # 10 items over 3 slots
+    assert len({t for calls in seen.values() for t, _ in calls}) == 3        # one thread per slot, always the same
+    assert pool.each(lambda slot: slot * 2) == [0, 2, 4]
+    pool.close()
+
+
+def test_visible_devices_parsing(monkeypatch):
+    monkeypatch.setenv("YB_DEVICES", "2, 0")
+    assert sharding.visible_devices() == [2, 0]
+    monkeypatch.delenv("YB_DEVICES")
+    monkeypatch.setenv("YB_DEVICE", "1")
+    assert sharding.visible_devices() == [1]
+    monkeypatch.delenv("YB_DEVICE")
+    assert sharding.visible_devices() == [0]                      # no GPU here: device 0 stays so the engine reports the CUDA error
