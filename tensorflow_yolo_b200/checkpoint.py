@@ -21,9 +21,13 @@ moving_variance}`` (net/layers.py:25,53-63); kernels are HWIO.  ``stream_from_ch
 darknet float stream ``base.load_weights`` consumes (net/base.py:26-46: OIHW kernels), so both weight sources feed the
 engine through the same entry point (yb_engine_load_weights).
 
-Parity note: TensorFlow is not installable in this environment, so the format is restated from its sources and
-checked by (a) round trips through the writer below, (b) the CRC-32C / masking / varint known-answer values of the
-LevelDB and TensorFlow test suites.  It is not pinned against a file written by TensorFlow itself.
+Parity note: TensorFlow is not installable in this environment, so no file written by TensorFlow itself exists to
+pin against.  The reader is checked against (a) tests/golden/bundle_tf_layout.ckpt.*, a two-shard checkpoint with Adam
+slot variables produced by oracle/make_golden_bundle.py -- an independent restatement of BundleWriter + the LevelDB
+table builder (shortened index separators, restart interval 16) whose protos are encoded by Google's protobuf
+runtime and whose CRCs are computed bit by bit; it shares no code with this module -- (b) literal bytes of that file
+(footer, index block, one data block) asserted in tests/test_checkpoint.py, (c) the CRC-32C / masking / varint
+known-answer values of the LevelDB and TensorFlow test suites, (d) round trips through the writer below.
 """
 import os
 import struct
@@ -47,6 +51,34 @@ _DT_OF_NP = {v: k for k, v in _NP_OF_DT.items()}
 
 class CheckpointError(Exception):
     pass
+
+
+_crc_table = None
+
+
+def crc32c_py(data, seed=0):
+    """CRC-32C in plain Python (byte-wise table): what _crc32c falls back to when libyolo_b200.so cannot be loaded, so
+    that a checkpoint can be listed / verified / converted on a machine without the CUDA library."""
+    global _crc_table
+    if _crc_table is None:
+        table = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ (0x82F63B78 if c & 1 else 0)
+            table.append(c)
+        _crc_table = table
+    crc = seed ^ 0xFFFFFFFF
+    for b in bytes(data):
+        crc = (crc >> 8) ^ _crc_table[(crc ^ b) & 0xFF]
+    return crc ^ 0xFFFFFFFF
+
+
+def _crc32c(data):
+    try:
+        return _lib.crc32c(data)
+    except (ImportError, OSError, AttributeError):
+        return crc32c_py(data if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data).tobytes())
 
 
 def mask_crc(crc):
@@ -158,7 +190,7 @@ def _read_block(data, offset, size, verify):
     ctype = data[offset + size]
     if verify:
         stored = struct.unpack_from("<I", data, offset + size + 1)[0]
-        actual = _lib.crc32c(bytes(data[offset:offset + size + 1]))
+        actual = _crc32c(bytes(data[offset:offset + size + 1]))
         if unmask_crc(stored) != actual:
             raise CheckpointError("index block at {} fails its CRC-32C".format(offset))
     if ctype != 0:
@@ -261,7 +293,7 @@ class BundleReader(object):
         if e.offset < 0 or e.offset + e.size > shard.size:
             raise CheckpointError("{}: bytes [{}, +{}] outside its data shard".format(name, e.offset, e.size))
         raw = np.array(shard[e.offset:e.offset + e.size])        # copy out of the mapping
-        if self.verify and unmask_crc(e.crc32c) != _lib.crc32c(raw):
+        if self.verify and unmask_crc(e.crc32c) != _crc32c(raw):
             raise CheckpointError("{}: tensor bytes fail their CRC-32C".format(name))
         return raw.view(dt).reshape(e.shape)
 
@@ -294,7 +326,7 @@ class _BlockBuilder(object):
 
 def _write_block(out, contents):
     offset = len(out)
-    trailer_crc = mask_crc(_lib.crc32c(contents + b"\x00"))
+    trailer_crc = mask_crc(_crc32c(contents + b"\x00"))
     out += contents + b"\x00" + struct.pack("<I", trailer_crc)
     return offset, len(contents)
 
@@ -315,7 +347,7 @@ def write_bundle(prefix, tensors, block_size=262144):
             raw = arr.astype(dt, copy=False).tobytes(order="C")
             f.write(raw)
             entries.append((name.encode("utf-8"), BundleEntry(_DT_OF_NP[np.dtype(dt)], arr.shape, 0, offset, len(raw),
-                                                              mask_crc(_lib.crc32c(raw)))))
+                                                              mask_crc(_crc32c(raw)))))
             offset += len(raw)
     header = b"\x08\x01" + b"\x1a\x02\x08\x01"            # num_shards = 1, version { producer: 1 }
     out = bytearray()

@@ -128,3 +128,102 @@ def test_restore_or_fall_back_like_the_reference(tmp_path, capsys, lib_built):
     # Saver.save writes what restore reads
     pbase.Saver().save(sess, str(tmp_path / "again.ckpt"))
     assert np.array_equal(ckpt.stream_from_checkpoint(net, str(tmp_path / "again.ckpt")), stream)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fixtures that this package's writer did NOT produce (oracle/make_golden_bundle.py: protobuf runtime + an independent
+# LevelDB table builder with shortened separators; two data shards; Adam slot variables)
+# ---------------------------------------------------------------------------------------------------------------
+FIXTURE = os.path.join(helpers.GOLDEN, "bundle_tf_layout.ckpt")
+
+
+def _three_conv_net():
+    from tensorflow_yolo_b200.net import layers as L
+    L.conv2d_bn_act.reset()
+    graph = L.reset_default_graph()
+    net = [L.input_layer([None, 32, 32, 3], "input")]
+    net.append(L.conv2d_bn_act(net[-1].out, 8, 3))
+    net.append(L.conv2d_bn_act(net[-1].out, 16, 3, 2))
+    net.append(L.conv2d_bn_act(net[-1].out, 4, 1, use_batch_normalization=False, activation_fn="linear"))
+    state = pbase.NetworkState(graph, "v3", 1, input_shape=(32, 32, 3))
+    graph._yb_state = state
+    net[0]._yb_state = state
+    return net
+
+
+def test_reads_checkpoint_not_written_by_own_writer(lib_built):
+    exp = {k.replace("|", "/"): v for k, v in np.load(os.path.join(helpers.GOLDEN, "bundle_expected.npz")).items()}
+    r = ckpt.BundleReader(FIXTURE)
+    assert r.header == {"num_shards": 2, "endianness": 0}
+    assert r.names() == sorted(exp) and len(exp) == 31
+    for name, want in exp.items():
+        got = r.get_tensor(name)
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), name
+    assert {r.entries[n].shard_id for n in exp} == {0, 1}            # both .data-0000i-of-00002 files are used
+    # the TEST path (net/yolo.py:71-78): only layer.variable_names are read; Adam slots, beta*_power, global_step are ignored
+    net = _three_conv_net()
+    stream = ckpt.stream_from_checkpoint(net, FIXTURE)
+    parts = []
+    for i, bn in ((0, True), (1, True), (2, False)):
+        stem = "yolo/conv2d_bn_act_%d/" % i
+        for leaf in (["beta", "gamma", "moving_mean", "moving_variance"] if bn else ["bias"]):
+            parts.append(exp[stem + leaf].reshape(-1))
+        parts.append(np.transpose(exp[stem + "kernel"], (3, 2, 0, 1)).reshape(-1))       # HWIO -> OIHW (net/base.py:36-40)
+    assert np.array_equal(stream, np.concatenate(parts)) and stream.size == P.weight_count(net[0]._yb_state.graph.specs)
+
+
+def test_fixture_bytes_are_the_documented_layout():
+    """Literal bytes of the independently produced .index, field by field (LevelDB table_format.md, tensor_bundle.proto)."""
+    data = open(FIXTURE + ".index", "rb").read()
+    # footer: metaindex handle (offset 1061, size 8), index handle (offset 1074, size 102) as varint64s, zero padding to
+    # 40 bytes, magic 0xdb4775248b80fb57 little-endian
+    assert data[-48:].hex() == "a50808b20866" + "00" * 34 + "57fb808b247547db"
+    # index block: restart interval 1; keys are SHORTENED separators -- "yolo/conv2d_bn_act_0/moving_n" sits between
+    # .../moving_mean and .../moving_variance, "z" is the short successor of the last key -- values are block handles
+    idx = data[1074:1074 + 102]
+    keys = [k for k, _ in ckpt._block_entries(idx)]
+    assert keys == [b"yolo/conv2d_bn_act_0/moving_n", b"yolo/conv2d_bn_act_1/moving_variance", b"z"]
+    assert struct.unpack("<I", idx[-4:])[0] == 3                                  # three restart points
+    # first data block, first entries: shared=0 non_shared=0 value_len=6 | key "" | BundleHeaderProto
+    #   08 02 = num_shards: 2;   1a 02 08 01 = version { producer: 1 }   (endianness LITTLE = 0 is not serialised)
+    assert data[:9].hex() == "000006" + "08021a020801"
+    # second entry: shared=0 non_shared=11 value_len=11 | "beta1_power" | BundleEntryProto
+    #   08 01 dtype DT_FLOAT | (shape: scalar, empty message omitted) | 18 01 shard_id 1 | (offset 0 omitted) | 28 04 size 4 |
+    #   35 <fixed32> masked crc32c
+    assert data[9:12].hex() == "000b0b" and data[12:23] == b"beta1_power"
+    assert data[23:30].hex() == "08011801280435"
+    value = np.asarray(0.9 ** 40, dtype=np.float32).tobytes()
+    assert struct.unpack("<I", data[30:34])[0] == ckpt.mask_crc(ckpt.crc32c_py(value))
+    # third entry shares the 4-byte prefix "beta" with its predecessor: shared=4 non_shared=7 ("2_power")
+    assert data[34:37].hex() == "04070d" and data[37:44] == b"2_power"
+    # block trailer: compression type 0 + masked CRC-32C over contents and type
+    handles = [v for _, v in ckpt._block_entries(idx)]
+    off, q = ckpt._get_varint(handles[0], 0)
+    size, _ = ckpt._get_varint(handles[0], q)
+    assert (off, data[off + size]) == (0, 0)
+    assert struct.unpack("<I", data[off + size + 1:off + size + 5])[0] == ckpt.mask_crc(ckpt.crc32c_py(data[off:off + size + 1]))
+
+
+def test_fixture_corruption_and_missing_shard_are_detected(tmp_path, lib_built):
+    import shutil
+    for ext in (".index", ".data-00000-of-00002", ".data-00001-of-00002"):
+        shutil.copy(FIXTURE + ext, str(tmp_path / ("c.ckpt" + ext)))
+    prefix = str(tmp_path / "c.ckpt")
+    blob = bytearray(open(prefix + ".data-00001-of-00002", "rb").read())
+    blob[100] ^= 0x40
+    open(prefix + ".data-00001-of-00002", "wb").write(bytes(blob))
+    r = ckpt.BundleReader(prefix)
+    bad = [n for n in r.names() if r.entries[n].shard_id == 1 and r.entries[n].offset <= 100 < r.entries[n].offset + r.entries[n].size]
+    assert len(bad) == 1
+    with pytest.raises(ckpt.CheckpointError, match="CRC"):
+        r.get_tensor(bad[0])
+    os.remove(prefix + ".data-00000-of-00002")
+    with pytest.raises(ckpt.CheckpointError, match="does not exist"):
+        ckpt.BundleReader(prefix).get_tensor("global_step")
+
+
+def test_pure_python_crc32c_matches_native(lib_built):
+    data = np.random.RandomState(1).bytes(4099)
+    assert ckpt.crc32c_py(b"123456789") == 0xe3069283 and ckpt.crc32c_py(bytes(32)) == 0x8a9136aa
+    assert ckpt.crc32c_py(data) == _lib.crc32c(data)
+    assert ckpt.crc32c_py(data[100:], seed=ckpt.crc32c_py(data[:100])) == ckpt.crc32c_py(data)

@@ -180,7 +180,7 @@ def test_detection_agreement_with_fp32_oracle_416():
     eng.close()
     ref_head = convstack.forward(topo, stream, x)
     geo = convstack.yolo_geometry(topo, shape)
-    flips, kept_total, matched = 0, 0, 0
+    flips, kept_total, matched, worst_wh = 0, 0, 0, 0.0
     for i in range(n):
         # (a) candidate sets away from the threshold band
         obj_gpu = 1. / (1. + np.exp(-head[i, :, 4].astype(np.float64)))
@@ -200,11 +200,15 @@ def test_detection_agreement_with_fp32_oracle_416():
             matched += 1
             got = np.asarray([d["x"], d["y"], d["w"], d["h"], d["prob"]], dtype=np.float64)
             exp = np.asarray([ref["x"][k], ref["y"][k], ref["w"][k], ref["h"][k], ref["prob"][k]], dtype=np.float64)
-            assert np.all(np.abs(got - exp) <= 2e-2 * np.maximum(np.abs(exp), 1.0)), (i, int(d["row"]), got, exp)
+            # x, y, prob are bounded functions of a head value: 2e-2 absolute.  w, h = anchor * exp(t): an absolute head
+            # error d is a RELATIVE size error exp(d) - 1, so they get 8e-2 relative (d up to ~0.08 on |t| of a few units)
+            assert np.all(np.abs(got - exp)[[0, 1, 4]] <= 2e-2), (i, int(d["row"]), got, exp)
+            assert np.all(np.abs(got - exp)[[2, 3]] <= 8e-2 * np.abs(exp)[[2, 3]]), (i, int(d["row"]), got, exp)
+            worst_wh = max(worst_wh, float(np.max(np.abs(got - exp)[[2, 3]] / np.abs(exp)[[2, 3]])))
     rate = flips / float(max(kept_total, 1))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "detection_flip_rate.json"), "w") as f:
             json.dump({"images": n, "kept_union": kept_total, "flips": flips, "flip_rate": rate, "matched": matched,
-                       "threshold": thr, "band": BAND}, f)
+                       "threshold": thr, "band": BAND, "worst_rel_error_w_h": worst_wh}, f)
     assert matched >= 10 and rate <= 0.25, (matched, rate)
