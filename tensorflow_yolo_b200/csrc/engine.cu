@@ -176,6 +176,7 @@ struct PostCtx {
   size_t dets_cap = 0;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   bool smem_set = false;
+  bool bulk_attr_set = false;     // per context (= per device): opt-in shared memory of decode_v3_bulk_kernel
 
   int alloc(int max_batch_, int rows_, int box_len_, int v2_) {
     max_batch = max_batch_; rows = rows_; box_len = box_len_; v2 = v2_;
@@ -213,8 +214,27 @@ struct PostCtx {
     for (int i = 0; i < n_scales; ++i) a.sc[i] = sc[i];
     a.n_scales = n_scales; a.rows = rows; a.box_len = box_len; a.n_images = n; a.v2 = v2; a.thr = thr;
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    if (!v2) {       // one lane per row (+ cooperative decode of the candidates)
-      decode_v3_kernel<<<ceil_div((long long)n * rows, 256), 256, 0, st>>>(a);
+    if (!v2) {
+      // Dense candidate sets on a contiguous [n * rows][5 + C] tensor (yb_post_run's layout; BASELINE config 5) take the
+      // bulk kernel: whole rows staged through shared memory, one lane per row.  Sparse sets (real detections: a few
+      // candidates per image) keep the kernel that touches one 32-byte sector per non-candidate row.  The choice is made
+      // from the score threshold (a low threshold is what makes a head dense); YB_DECODE_BULK = 0 / 1 forces it.
+      bool contiguous = (reinterpret_cast<uintptr_t>(sc[0].base) & 15) == 0 && sc[0].row_begin == 0;
+      for (int i = 0; i < n_scales && contiguous; ++i)
+        contiguous = sc[i].base == sc[0].base + (long long)sc[i].row_begin * box_len && sc[i].cell_stride == sc[i].na * box_len &&
+                     sc[i].img_stride == (long long)rows * box_len;
+      const char* force = getenv("YB_DECODE_BULK");
+      const bool bulk = contiguous && (force ? atoi(force) != 0 : thr < 0.02f);
+      const int bulk_smem = DECODE_BULK_WARPS * 32 * box_len * 4;
+      if (bulk && bulk_smem <= 100 * 1024) {
+        if (!bulk_attr_set) {
+          YB_CUDA(cudaFuncSetAttribute(decode_v3_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+          bulk_attr_set = true;
+        }
+        decode_v3_bulk_kernel<<<ceil_div((long long)n * rows, DECODE_BULK_WARPS * 32), DECODE_BULK_WARPS * 32, bulk_smem, st>>>(a, sc[0].base);
+      } else {       // one lane per row (+ cooperative decode of the candidates)
+        decode_v3_kernel<<<ceil_div((long long)n * rows, 256), 256, 0, st>>>(a);
+      }
     } else {         // one warp per row: the softmax score needs the whole row anyway
       const long long warps = (long long)n * rows;
       decode_kernel<<<ceil_div(warps * 32, 256), 256, 0, st>>>(a);
@@ -1056,7 +1076,11 @@ static int compile_plan(yb_engine* e) {
         op.bn_max = bn;
         op.cfg = default_cfg(op, e->max_batch, e->cta_pairs);
       } else {
+        // No silent detour: the CUDA-core kernel is a debug cross-check, an order of magnitude slower than the tcgen05 path.
         op.path = PATH_SIMT;
+        fprintf(stderr, "libyolo_b200: warning: layer %d (conv %dx%d s%d, %d -> %d channels, input pitch %d, channel offset %d) does not "
+                        "meet the TMA alignment rules (channels %% 32, pitches and offsets %% 8) and runs on the CUDA-core conv kernel\n",
+                i, l.ksize, l.ksize, l.stride, op.cin, op.cout, op.in.ld, op.in.coff);
       }
       op.cout_pad = round_up(op.cout, (op.path == PATH_TC || op.path == PATH_FUSED) ? op.bn_max : 4);
       emit = true;

@@ -208,12 +208,14 @@ __global__ void __launch_bounds__(256) decode_v3_kernel(const DecodeArgs a) {
     // per lane: smallest d = 1 + exp(-t) of its classes (lowest index on ties) and the runner-up
     float dmin = INFINITY, d2 = INFINITY;
     int kmin = 0x7fffffff;
+    bool saw_nan = false;            // a NaN logit is np.argmax's maximum: it must reach the exact path, not be skipped
     if (my_src >= 0) {
 #pragma unroll 5
       for (int k = 5 + sl; k < len; k += 8) {
         // fast exponential (two instructions instead of eight): the ranking only has to be right up to the tie band
         // below, which is far wider than its error (|t| * 1.2e-7 + 2^-22 relative, |t| < 88 where d is finite and > 1)
         const float d = __fadd_rn(1.0f, __expf(-__ldg(rp + k)));
+        saw_nan |= (d != d);
         if (d < dmin) { d2 = dmin; dmin = d; kmin = k - 5; }
         else if (d < d2) d2 = d;
       }
@@ -231,29 +233,161 @@ __global__ void __launch_bounds__(256) decode_v3_kernel(const DecodeArgs a) {
     // once 1/d is subnormal.  Rare (band 1e-4 relative): only then are the exact quotients computed, with the accurate
     // exponential (by the eight lanes of that row).
     const float near = wd * 1.0001f;
-    const bool tie = my_src >= 0 && ((kmin != wk && dmin <= near) || (d2 <= near) || !(wd < 1e37f));
+    const bool tie = my_src >= 0 && (saw_nan || (kmin != wk && dmin <= near) || (d2 <= near) || !(wd < 1e37f));
     const unsigned ties = __ballot_sync(0xffffffffu, tie);
     int best_k = wk;
     if (ties & gmask) {
       // the reference's own arithmetic: first index of the largest 1 / (1 + exp(-t)) in float32
       float smax = -1.0f;
       int cand_k = 0x7fffffff;
+      bool any_nan = false;                                        // np.argmax: the first NaN is the maximum
       if (my_src >= 0) {
         for (int k = 5 + sl; k < len; k += 8) {
           const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__ldg(rp + k))));
-          if (sg > smax) { smax = sg; cand_k = k - 5; }          // ascending k: a later equal value never replaces
+          if (sg != sg) { if (!any_nan) { any_nan = true; cand_k = k - 5; } }
+          else if (!any_nan && sg > smax) { smax = sg; cand_k = k - 5; }          // ascending k: a later equal value never replaces
         }
       }
 #pragma unroll
       for (int sft = 4; sft > 0; sft >>= 1) {
         const float os = __shfl_xor_sync(gmask, smax, sft);
         const int ok = __shfl_xor_sync(gmask, cand_k, sft);
-        if (os > smax || (os == smax && ok < cand_k)) { smax = os; cand_k = ok; }
+        const bool on = __shfl_xor_sync(gmask, any_nan, sft);
+        const bool take = (on != any_nan) ? on : (on ? ok < cand_k : (os > smax || (os == smax && ok < cand_k)));
+        if (take) { smax = os; cand_k = ok; any_nan = on; }
       }
       best_k = cand_k;
     }
     if (my_src >= 0 && sl == 0) a.cls[warp_first + my_src] = best_k;
   }
+}
+
+// YOLOv3 decode for DENSE candidate sets on a contiguous head tensor [n_images * rows][5 + C] (the stand-alone layout of
+// yb_post_run, BASELINE config 5: score threshold 0.001, every row a candidate).  The kernel above reads a row with
+// eight lanes and 4-byte loads and is issue-bound at ~75 warp instructions per row; here a warp stages its 32 rows
+// (32 * len * 4 bytes, contiguous and 16-byte aligned because the slab starts at a multiple of 32 rows) in shared memory
+// with 16-byte loads and then works one lane per row:
+//   * the class argmax needs no exponential: sigmoid is monotone, so argmax sigmoid(t) = argmax t unless the two largest
+//     logits are so close -- or so saturated -- that their float32 sigmoids could round to the same value, in which case
+//     np.argmax's "first of the maxima" is decided by the reference's own arithmetic, computed by the whole warp for that
+//     row.  Separation bound: the computed sigmoid (expf <= 2 ulp, one add, one division) is within 2.4e-7 relative of
+//     the true one, and sigmoid(a) / sigmoid(b) = 1 + (1 - sigmoid(a)) (e^(a-b) - 1) >= 1 + 9.1e-4 * 1e-3 for
+//     a - b >= 1e-3 and a <= 7, four times the rounding noise.  Outside [-80, 7], or with a NaN in the row: exact path.
+//   * rows are `len` words apart: an odd len (85) makes the lane-per-row reads bank-conflict free.
+constexpr int DECODE_BULK_WARPS = 4;
+__global__ void __launch_bounds__(DECODE_BULK_WARPS * 32) decode_v3_bulk_kernel(const DecodeArgs a, const float* __restrict__ head) {
+  extern __shared__ __align__(16) float bulk_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int len = a.box_len;
+  float* slab = bulk_smem + (size_t)warp * 32 * len;
+  const long long total = (long long)a.n_images * a.rows;
+  const long long warp_first = ((long long)blockIdx.x * DECODE_BULK_WARPS + warp) << 5;
+  if (warp_first >= total) return;
+  const int n_rows = (int)((total - warp_first < 32) ? (total - warp_first) : 32);
+  const float* src = head + warp_first * len;
+  const int words = n_rows * len;
+  {
+    // asynchronous 16-byte copies straight into shared memory: the whole slab (10.9 KB at len = 85) is in flight at once
+    const int vec = words >> 2;                     // warp_first * len * 4 bytes is a multiple of 16: 32 rows per slab
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab);
+    for (int i = lane; i < vec; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + 4 * i) : "memory");
+    for (int i = (vec << 2) + lane; i < words; i += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)i * 4u), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncwarp();
+  const long long gr = warp_first + lane;
+  const bool live = lane < n_rows;
+  const float* my = slab + lane * len;
+  bool cand = false, tie = false;
+  int best_k = 0;
+  if (live) {
+    const int img = (int)(gr / a.rows);
+    const int row = (int)(gr - (long long)img * a.rows);
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < POST_MAX_SCALES; ++i)
+      if (i < a.n_scales && row >= a.sc[i].row_begin) s = i;
+    const ScaleDesc& sc = a.sc[s];
+    const int local = row - sc.row_begin;
+    const int cell = local / sc.na;
+    const int anc = local - cell * sc.na;
+    const float obj = sigmoid_ref(my[4]);
+    cand = obj >= a.thr;
+    a.prob[gr] = cand ? obj : __int_as_float(0x7fc00000);
+    if (cand) {
+      const int cy = cell / sc.w;
+      const int cx = cell - cy * sc.w;
+      a.x[gr] = __fdiv_rn(__fadd_rn(sigmoid_ref(my[0]), (float)cx), (float)sc.w);
+      a.y[gr] = __fdiv_rn(__fadd_rn(sigmoid_ref(my[1]), (float)cy), (float)sc.h);
+      a.w[gr] = __ddiv_rn(__dmul_rn((double)sc.anchors[2 * anc], (double)expf(my[2])), (double)sc.w);
+      a.h[gr] = __ddiv_rn(__dmul_rn((double)sc.anchors[2 * anc + 1], (double)expf(my[3])), (double)sc.h);
+      // four independent (max, runner-up, index) trackers over k mod 4 keep the compare chains short; merged afterwards
+      // with the lower index winning among equal logits (np.argmax: the first of the maxima)
+      float m1[4], m2[4];
+      int bk[4];
+      bool nan = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { m1[j] = -INFINITY; m2[j] = -INFINITY; bk[j] = 0x7fffffff; }
+      int k = 5;
+      for (; k + 4 <= len; k += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t = my[k + j];
+          nan |= (t != t);
+          const bool gt = t > m1[j];                           // strict: the first of equal logits stays
+          m2[j] = gt ? m1[j] : fmaxf(m2[j], t);
+          bk[j] = gt ? k + j - 5 : bk[j];
+          m1[j] = gt ? t : m1[j];
+        }
+      }
+      for (int j = 0; k < len; ++k, ++j) {
+        const float t = my[k];
+        nan |= (t != t);
+        const bool gt = t > m1[j];
+        m2[j] = gt ? m1[j] : fmaxf(m2[j], t);
+        bk[j] = gt ? k - 5 : bk[j];
+        m1[j] = gt ? t : m1[j];
+      }
+      float top = m1[0], second = m2[0];
+      best_k = bk[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) {
+        const bool win = m1[j] > top || (m1[j] == top && bk[j] < best_k);
+        second = fmaxf(fmaxf(second, m2[j]), win ? top : m1[j]);
+        best_k = win ? bk[j] : best_k;
+        top = win ? m1[j] : top;
+      }
+      tie = nan || !(top - second >= 1e-3f) || !(top <= 7.0f) || !(top >= -80.0f);
+    }
+  }
+  // exact path for the rare near-tie rows: the reference's float32 sigmoids, first index of the largest, by all 32 lanes
+  unsigned ties = __ballot_sync(0xffffffffu, tie);
+  while (ties) {
+    const int r = __ffs(ties) - 1;
+    ties &= ties - 1;
+    const float* rp = slab + r * len;
+    float smax = -1.0f;
+    int cand_k = 0x7fffffff;
+    bool any_nan = false;
+    for (int k = 5 + lane; k < len; k += 32) {
+      const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rp[k])));
+      if (sg != sg) { if (!any_nan) { any_nan = true; cand_k = k - 5; } }        // np.argmax: the first NaN wins
+      else if (!any_nan && sg > smax) { smax = sg; cand_k = k - 5; }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, smax, sft);
+      const int ok = __shfl_xor_sync(0xffffffffu, cand_k, sft);
+      const bool on = __shfl_xor_sync(0xffffffffu, any_nan, sft);
+      const bool take = (on != any_nan) ? on : (on ? ok < cand_k : (os > smax || (os == smax && ok < cand_k)));
+      if (take) { smax = os; cand_k = ok; any_nan = on; }
+    }
+    if (lane == r) best_k = cand_k;
+  }
+  if (live && cand) a.cls[gr] = best_k;
 }
 
 // ----------------------------------------------------------------------------------------------

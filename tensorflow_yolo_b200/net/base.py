@@ -244,30 +244,28 @@ def run_kmeans(data, num_anchors, tolerate, verbose=False):
     return km.cluster_centers_
 
 
+def _voc_box(node, width, height, normalize):
+    """One <object> of a Pascal-VOC file as (x1, y1, x2, y2, name); corners divided by the image size on request."""
+    corners = {tag: int(node.find("bndbox").find(tag).text) for tag in ("xmin", "ymin", "xmax", "ymax")}
+    if normalize:
+        corners = {tag: v / (width if tag[0] == "x" else height) for tag, v in corners.items()}
+    return corners["xmin"], corners["ymin"], corners["xmax"], corners["ymax"], node.find("name").text
+
+
 def parse_annotations(annotation_dir, image_dir, normalize=False):
-    """Pascal-VOC XML files -> [(image path, [(x1, y1, x2, y2, name), ...])] (net/base.py:69-97)."""
+    """Pascal-VOC annotations of a directory, in os.listdir order like the reference (net/base.py:69-97):
+    [(image path, [(x1, y1, x2, y2, class name), ...]), ...]; with normalize the corners are fractions of the image."""
     import xml.etree.ElementTree as ET
-    annotations = [os.path.join(os.path.abspath(annotation_dir), f) for f in os.listdir(annotation_dir)
-                   if f.lower().endswith(".xml")]
-    result = []
-    for annotation in annotations:
-        root = ET.parse(annotation).getroot()
-        img_path = os.path.join(image_dir, root.find("filename").text)
-        size = root.find("size")
-        w = int(size.find("width").text)
-        h = int(size.find("height").text)
-        img_objects = []
-        for obj in root.findall("object"):
-            name = obj.find("name").text
-            bndbox = obj.find("bndbox")
-            x1, y1 = int(bndbox.find("xmin").text), int(bndbox.find("ymin").text)
-            x2, y2 = int(bndbox.find("xmax").text), int(bndbox.find("ymax").text)
-            if normalize:
-                x1, x2 = x1 / w, x2 / w
-                y1, y2 = y1 / h, y2 / h
-            img_objects.append((x1, y1, x2, y2, name))
-        result.append((img_path, img_objects))
-    return result
+    folder = os.path.abspath(annotation_dir)
+    out = []
+    for entry in os.listdir(annotation_dir):
+        if not entry.lower().endswith(".xml"):
+            continue
+        doc = ET.parse(os.path.join(folder, entry)).getroot()
+        width, height = (int(doc.find("size").find(tag).text) for tag in ("width", "height"))
+        boxes = [_voc_box(node, width, height, normalize) for node in doc.findall("object")]
+        out.append((os.path.join(image_dir, doc.find("filename").text), boxes))
+    return out
 
 
 def boxes_to_arrays(boxes):
@@ -307,14 +305,13 @@ def preprocess_image(image_path, new_shape, objects=None, augment_prob=0.):
 
 
 def generate_test_batch(img_paths, batch_size, input_shape):
-    total_batches = int(np.ceil(len(img_paths) / batch_size))
-    for b in range(total_batches):
-        images, paths = [], []
-        for i in range(min(batch_size, len(img_paths) - b * batch_size)):
-            image, _ = preprocess_image(img_paths[b * batch_size + i], input_shape, augment_prob=0.)
-            images.append(np.expand_dims(image, axis=0))
-            paths.append(img_paths[b * batch_size + i])
-        yield np.concatenate(images, axis=0), paths
+    """The reference's host-side feeder (net/base.py:158-168): consecutive groups of batch_size paths, each yielded as
+    (float64 [n, H, W, 3] RGB in [0, 1], the paths); the last group may be smaller."""
+    for first in range(0, len(img_paths), batch_size):
+        group = list(img_paths[first:first + batch_size])
+        # an unreadable file makes preprocess_image return None, which cannot be unpacked -- as in the reference
+        pixels = [preprocess_image(path, input_shape, augment_prob=0.)[0] for path in group]
+        yield np.stack(pixels, axis=0), group
 
 
 def generate_raw_batch(img_paths, batch_size):
@@ -372,18 +369,20 @@ def non_maximum_suppression(boxes, iou_threshold):
 
 
 def draw_boxes(path_to_img, boxes, class_names):
+    """The picture with one 3-pixel rectangle and a "<class> <score>" caption per box (net/base.py:212-226): corners
+    are the box scaled to the picture and clamped at 0, the colour cycles through COLORS by class index."""
     import cv2
     image = cv2.imread(path_to_img)
     assert image is not None
-    h, w = image.shape[0:2]
+    height, width = image.shape[:2]
     for box in boxes:
-        tl = np.maximum(box.get_top_left(h, w), 0)
-        br = np.maximum(box.get_bottom_right(h, w), 0)
-        tl, br = (int(tl[0]), int(tl[1])), (int(br[0]), int(br[1]))
-        color = COLORS[int(box.class_idx) % len(COLORS)]
-        cv2.rectangle(image, tl, br, color, thickness=3)
-        cv2.putText(image, "{} {:.3f}".format(class_names[int(box.class_idx)], float(box.prob)), (tl[0], tl[1] - 10),
-                    cv2.FONT_HERSHEY_SIMPLEX, 0.5, color, thickness=1)
+        cls = int(box.class_idx)
+        colour = COLORS[cls % len(COLORS)]
+        (left, top), (right, bottom) = ([int(max(v, 0)) for v in corner]
+                                        for corner in (box.get_top_left(height, width), box.get_bottom_right(height, width)))
+        cv2.rectangle(image, (left, top), (right, bottom), colour, thickness=3)
+        cv2.putText(image, "{} {:.3f}".format(class_names[cls], float(box.prob)), (left, top - 10), cv2.FONT_HERSHEY_SIMPLEX,
+                    0.5, colour, thickness=1)
     return image
 
 

@@ -53,15 +53,22 @@ def create_full_network(anchors, class_names, is_training, scope="yolo", input_s
     return net
 
 
+def _read_darknet_v2_header(f):
+    """16 bytes: int32 major, minor, revision, then a 4-byte `seen` counter -- float32 for format >= 0.2 (and sane
+    version numbers), int32 before (net/v2.py:68-77; the reference keeps it at 4 bytes in both cases)."""
+    major, minor, revision = (int(v) for v in np.fromfile(f, count=3, dtype=np.int32))
+    new_format = major * 10 + minor >= 2 and major < 1000 and minor < 1000
+    seen = np.fromfile(f, count=1, dtype=np.float32 if new_format else np.int32)
+    return (major, minor, revision), seen
+
+
 @staticmethod
 def load_weights(layers, weights_path):
     print("Reading pre-trained weights from {}".format(weights_path))
     with open(weights_path, "rb") as f:
-        major, minor, revision = np.fromfile(f, count=3, dtype=np.int32)
-        print("major, minor, revision: {}, {}, {}".format(major, minor, revision))
-        # the reference reads a 4-byte `seen` in both branches (net/v2.py:71-74)
-        seen_dtype = np.float32 if (major * 10 + minor) >= 2 and major < 1000 and minor < 1000 else np.int32
-        print("SEEN: ", np.fromfile(f, count=1, dtype=seen_dtype))
+        version, seen = _read_darknet_v2_header(f)
+        print("major, minor, revision: {}, {}, {}".format(*version))
+        print("SEEN: ", seen)
         weights = np.fromfile(f, dtype=np.float32)
     print("Found {} weight values.".format(len(weights)))
     return base.load_weights(layers, weights)
@@ -83,24 +90,15 @@ def find_bounding_boxes(net_out, net, threshold, iou_threshold, anchors, class_n
 
 @staticmethod
 def generate_anchors(params):
-    """ANCHOR mode (net/v2.py:298-323): k-means over the normalised (w, h) of every annotated box, scaled to grid
-    units of the network input (input_w / stride, input_h / stride).  Returns (flat anchors, set of class names)."""
-    num_anchors = int(params["num_anchors"])
-    image_dir = params["image_dir"]
-    annotation_dir = params["annotation_dir"]
-    tolerate = float(params["tolerate"])
-    stride = int(params["stride"])
-    input_w = int(params["input_w"])
-    input_h = int(params["input_h"])
-
-    annotations = base.parse_annotations(annotation_dir, image_dir, normalize=True)
+    """ANCHOR mode (net/v2.py:298-323): k-means over the normalised (width, height) of every annotated box; the
+    centres are scaled to grid units of the network input (input_w / stride by input_h / stride).
+    Returns (flat anchor array [w0, h0, w1, h1, ...], set of class names)."""
+    grid_w = int(params["input_w"]) / int(params["stride"])
+    grid_h = int(params["input_h"]) / int(params["stride"])
+    annotations = base.parse_annotations(params["annotation_dir"], params["image_dir"], normalize=True)
     print("{} annotations found.".format(len(annotations)))
-    class_names = set()
-    data = []
-    for annotation in annotations:
-        for o in annotation[1]:
-            data.append([float(o[2] - o[0]), float(o[3] - o[1])])
-            class_names.add(o[-1])
-    anchors = base.run_kmeans(data, num_anchors, tolerate)
-    anchors = [[a[0] * input_w / stride, a[1] * input_h / stride] for a in anchors]
-    return np.reshape(anchors, [-1]), class_names
+    boxes = [box for _, image_boxes in annotations for box in image_boxes]
+    sizes = [[float(x2 - x1), float(y2 - y1)] for x1, y1, x2, y2, _ in boxes]
+    class_names = {name for _, _, _, _, name in boxes}
+    centres = base.run_kmeans(sizes, int(params["num_anchors"]), float(params["tolerate"]))
+    return np.reshape([[cw * grid_w, ch * grid_h] for cw, ch in centres], [-1]), class_names

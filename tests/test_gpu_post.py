@@ -287,7 +287,45 @@ def test_nms_dense_config5_image_vs_oracle():
     assert np.array_equal(c["row"][postprocess.nms(c, 0.6)], kept[0]["row"])
 
 
-def test_decode_class_argmax_near_ties():
+@pytest.mark.parametrize("bulk", ["0", "1"])
+def test_decode_class_argmax_near_ties(bulk, monkeypatch):
+    monkeypatch.setenv("YB_DECODE_BULK", bulk)        # 1: the dense kernel (rows staged in shared memory, argmax on raw logits)
+    _near_ties_case()
+
+
+def test_bulk_decode_equals_row_kernel_bit_for_bit(monkeypatch):
+    """The two v3 decode kernels (sparse: one sector per row + cooperative candidates; bulk: dense heads, config 5) must
+    produce identical candidates -- every field bit for bit -- on random heads, with NaN / inf logits, at a row count
+    that is not a multiple of the 32-row slabs, for thresholds on both sides of the automatic switch."""
+    shape = (96, 96, 3)                                   # R = 3 * (9 + 36 + 144) = 567 rows per image
+    rs = np.random.RandomState(5)
+    head = rs.normal(0, 2.0, (3, 567, 85)).astype(np.float32)
+    head[0, 10, 5:] = np.nan
+    head[0, 11, 17] = np.nan
+    head[1, 3, 5:9] = np.inf
+    head[1, 4, 5:] = -np.inf
+    head[2, 5, 40] = 7.5
+    head[2, 6, 5:] = -85.0
+    post = _post_v3(shape, 3)
+    for thr in (0.001, 0.3):
+        out = {}
+        for bulk in ("0", "1"):
+            monkeypatch.setenv("YB_DECODE_BULK", bulk)
+            out[bulk] = post.decode(head, thr)
+        for i, (a, b) in enumerate(zip(out["0"], out["1"])):
+            assert len(a) == len(b) and len(a) > 100
+            for f in ("row", "class_idx", "prob", "x", "y", "w", "h"):
+                assert np.array_equal(a[f], b[f], equal_nan=True), f
+            with np.errstate(all="ignore"):              # both against numpy's argmax (first NaN / first of equal maxima)
+                ref = postprocess.decode_v3_image(head[i], _geo(shape), thr)
+            assert np.array_equal(a["row"], ref["row"]) and np.array_equal(a["class_idx"], ref["class_idx"])
+        monkeypatch.delenv("YB_DECODE_BULK")
+        auto = post.decode(head, thr)
+        for a, b in zip(out["0"], auto):
+            assert np.array_equal(a["class_idx"], b["class_idx"]) and np.array_equal(a["row"], b["row"])
+
+
+def _near_ties_case():
     """np.argmax(sigmoid(t)) with classes a few float32 ulps apart, equal, saturated (sigmoid == 1 for many classes) and
     tiny (subnormal sigmoids): the device ranks classes on 1 + exp(-t) with the fast exponential and has to fall back to the
     exact quotients whenever that ranking cannot be trusted; the first of the maxima wins, as in numpy."""
