@@ -147,13 +147,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int FIRST_ROWS = 8;     // output rows per block (one per warp)
+constexpr int FIRST_ROWS_PLAIN = 8;     // output rows per block (one per warp; two per warp in the pooled variant)
+constexpr int FIRST_ROWS = FIRST_ROWS_PLAIN;
 // shared-memory elements per staged row: 4 leading (1 unused + left halo), W*3 image, 8 trailing (right halo + padded k)
 #define FIRST_ROW_ELEMS(W) ((W) * 3 + 12)
 
-template <bool U8>
+// POOL: the 2x2/2 max pool that follows the first conv of Darknet-19 (net/v2.py:20-22, net/layers.py:70-81) is applied
+// in registers -- a warp computes two adjacent output rows, takes the vertical maximum in place and the horizontal one
+// with a shuffle (pixels x and x+1 sit four lanes apart) -- and only the pooled map is written: the 416^2 x 32 activation
+// (1.4 GB per 128 images) never exists.  max commutes with the monotone bf16 rounding, so the result is bit-identical to
+// conv -> bf16 -> maxpool2_kernel.
+template <bool U8, bool POOL>
 __device__ __forceinline__ void conv_first_mma_body(const InView& in, const float* __restrict__ wt, const ConvArgs& a,
                                                     const float* __restrict__ u8_lut, int n_row_groups) {
+  constexpr int FIRST_ROWS = POOL ? 2 * FIRST_ROWS_PLAIN : FIRST_ROWS_PLAIN;     // output rows per block
   // Shared memory: FIRST_ROWS + 2 input rows of one image as bf16, each with a one-pixel zero halo left and
   // right (rows outside the image are zero), so the gather below needs no bounds checks at all.
   extern __shared__ __align__(16) uint16_t s_in[];
@@ -247,6 +254,68 @@ __device__ __forceinline__ void conv_first_mma_body(const InView& in, const floa
       s_in[r * row_elems + (e < 4 ? e : 4 + row_in + (e - 4))] = 0;
     }
     __syncthreads();
+    if (POOL) {
+      const int ya = y0 + 2 * warp;                        // output rows ya, ya + 1 -> pooled row ya / 2 (H is even)
+      if (ya < H) {
+        const int Wp = W >> 1;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) + ((long long)img * (H >> 1) + (ya >> 1)) * Wp * a.out_ld + c0 + 8 * t;
+        for (int xt = 0; xt < n_xt; ++xt) {
+          uint32_t pk[2][2][4];                            // [row a / b][pixel g / g+8][4 channel pairs]
+#pragma unroll
+          for (int rw = 0; rw < 2; ++rw) {
+            const uint16_t* srow = s_in + (2 * warp + rw) * row_elems;
+            uint32_t afrag[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              int x = xt * 16 + g + r * 8;
+              x = x < W ? x : W - 1;
+              const uint16_t* p = srow + x * 3;
+              uint32_t v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = p[soff[j]];
+              afrag[0][r] = v[0] | (v[1] << 16);
+              afrag[0][r + 2] = v[2] | (v[3] << 16);
+              afrag[1][r] = v[4] | (v[5] << 16);
+              afrag[1][r + 2] = v[6] | (v[7] << 16);
+            }
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f; }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], afrag[ks], bf[ks][nt][0], bf[ks][nt][1]);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                float y0v = acc[nt][2 * r] * sc[2 * nt] + sh[2 * nt];
+                float y1v = acc[nt][2 * r + 1] * sc[2 * nt + 1] + sh[2 * nt + 1];
+                if (a.leaky) { y0v = fmaxf(y0v, 0.1f * y0v); y1v = fmaxf(y1v, 0.1f * y1v); }
+                pk[rw][r][nt] = pack_bf16(y0v, y1v);
+              }
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            uint32_t m[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              __nv_bfloat162 va = *reinterpret_cast<__nv_bfloat162*>(&pk[0][r][nt]);
+              __nv_bfloat162 vb = *reinterpret_cast<__nv_bfloat162*>(&pk[1][r][nt]);
+              __nv_bfloat162 vm = __hmax2(va, vb);                                        // rows ya, ya + 1
+              uint32_t um = *reinterpret_cast<uint32_t*>(&vm);
+              const uint32_t other = __shfl_xor_sync(0xffffffffu, um, 4);                 // pixel x ^ 1 (lane = g * 4 + t)
+              __nv_bfloat162 vo = *reinterpret_cast<const __nv_bfloat162*>(&other);
+              vm = __hmax2(vm, vo);
+              m[nt] = *reinterpret_cast<uint32_t*>(&vm);
+            }
+            const int x = xt * 16 + g + r * 8;
+            if (!(g & 1) && x < W) *reinterpret_cast<uint4*>(orow + (long long)(x >> 1) * a.out_ld) = make_uint4(m[0], m[1], m[2], m[3]);
+          }
+        }
+      }
+      continue;
+    }
     const int y = y0 + warp;
     if (y < H) {
       const uint16_t* srow = s_in + warp * row_elems;      // smem row `warp` is input row y-1
@@ -291,21 +360,31 @@ __device__ __forceinline__ void conv_first_mma_body(const InView& in, const floa
   }
 }
 
-// Two entry points so that each variant keeps three resident blocks per SM (the grid is exactly one resident wave): the
-// float variant compiles to 80 registers as it is, the uint8 variant needs the bound (84 registers made it two blocks
-// per SM: 0.47 ms per 128 images against 0.36 ms for the float input, which moves four times the bytes).
-template <bool U8>
+// Entry points per (input type, pooled) so that each variant keeps its own register bound: the float variant compiles to
+// 80 registers as it is, the uint8 variant needs the bound (84 registers made it two blocks per SM: 0.47 ms per 128
+// images against 0.36 ms for the float input, which moves four times the bytes).
+template <bool U8, bool POOL>
 __global__ void conv_first_mma_kernel(const InView in, const float* __restrict__ wt, const ConvArgs a,
                                       const float* __restrict__ u8_lut, int n_row_groups);
 template <>
-__global__ void __launch_bounds__(256) conv_first_mma_kernel<false>(const InView in, const float* __restrict__ wt, const ConvArgs a,
-                                                                   const float* __restrict__ u8_lut, int n_row_groups) {
-  conv_first_mma_body<false>(in, wt, a, u8_lut, n_row_groups);
+__global__ void __launch_bounds__(256) conv_first_mma_kernel<false, false>(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                                          const float* __restrict__ u8_lut, int n_row_groups) {
+  conv_first_mma_body<false, false>(in, wt, a, u8_lut, n_row_groups);
 }
 template <>
-__global__ void __launch_bounds__(256, 3) conv_first_mma_kernel<true>(const InView in, const float* __restrict__ wt, const ConvArgs a,
-                                                                     const float* __restrict__ u8_lut, int n_row_groups) {
-  conv_first_mma_body<true>(in, wt, a, u8_lut, n_row_groups);
+__global__ void __launch_bounds__(256, 3) conv_first_mma_kernel<true, false>(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                                            const float* __restrict__ u8_lut, int n_row_groups) {
+  conv_first_mma_body<true, false>(in, wt, a, u8_lut, n_row_groups);
+}
+template <>
+__global__ void __launch_bounds__(256, 2) conv_first_mma_kernel<false, true>(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                                            const float* __restrict__ u8_lut, int n_row_groups) {
+  conv_first_mma_body<false, true>(in, wt, a, u8_lut, n_row_groups);
+}
+template <>
+__global__ void __launch_bounds__(256, 2) conv_first_mma_kernel<true, true>(const InView in, const float* __restrict__ wt, const ConvArgs a,
+                                                                           const float* __restrict__ u8_lut, int n_row_groups) {
+  conv_first_mma_body<true, true>(in, wt, a, u8_lut, n_row_groups);
 }
 
 // ---- plain CUDA-core conv on the packed bf16 operands: wt [cout_pad][taps*Cin] ----

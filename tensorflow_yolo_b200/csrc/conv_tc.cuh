@@ -30,7 +30,7 @@
 
 namespace yb {
 
-enum OutMode { OUT_PLAIN = 0, OUT_UPSAMPLE2 = 1, OUT_REORG2 = 2 };
+enum OutMode { OUT_PLAIN = 0, OUT_UPSAMPLE2 = 1, OUT_REORG2 = 2, OUT_POOL2 = 3 };     // OUT_POOL2: first conv (mma.sync) only
 
 struct ConvArgs {
   int M;              // valid output pixels = n * Ho * Wo

@@ -525,7 +525,8 @@ struct yb_engine {
   bool pdl = true;              // programmatic dependent launch between consecutive tcgen05 convs
   bool fuse_upsample = true;    // conv epilogue writes the 2x2 replicas itself (YB_FUSE_UPSAMPLE=0: separate copy kernel)
   int fuse_stem = 1, fuse_block = 1;   // conv_fused.cuh (YB_FUSE_STEM / YB_FUSE_BLOCK: 0 = off, 1 = on unless YB_KEEP_ALL, 2 = always)
-  int first_resident[2] = {1, 1};      // co-resident blocks per SM of conv_first_mma_kernel<float / uint8>
+  int first_resident[4] = {1, 1, 1, 1};   // co-resident blocks per SM of conv_first_mma_kernel<float / uint8> (+2: pooled variant)
+  int fuse_pool = 1;                   // first conv + 2x2 max pool in one kernel (YB_FUSE_POOL; off under YB_KEEP_ALL unless 2)
   int pixel_pairs = 1;          // Op::px_pair: 1 = the Cin=32 stride-1 convs (default), 2 = also the stride-2 one (measured
                                 // slower: 0.423 -> 0.441 ms, K grows by a third), 0 = plain views (YB_PIXEL_PAIRS)
   int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
@@ -763,14 +764,20 @@ static int set_kernel_attrs(yb_engine* e) {
   YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
   YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
   YB_CUDA(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_BLOCK));
-  const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2;
+  const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2, smem_pool = (2 * FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2;
   if (smem_first <= 200 * 1024) {
-    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[0], conv_first_mma_kernel<false>, 256, smem_first));
-    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[1], conv_first_mma_kernel<true>, 256, smem_first));
-    for (int i = 0; i < 2; ++i) if (e->first_resident[i] < 1) e->first_resident[i] = 1;
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[0], conv_first_mma_kernel<false, false>, 256, smem_first));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[1], conv_first_mma_kernel<true, false>, 256, smem_first));
   }
+  if (smem_pool <= 200 * 1024) {
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[2], conv_first_mma_kernel<false, true>, 256, smem_pool));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->first_resident[3], conv_first_mma_kernel<true, true>, 256, smem_pool));
+  }
+  for (int i = 0; i < 4; ++i) if (e->first_resident[i] < 1) e->first_resident[i] = 1;
   return YB_OK;
 }
 
@@ -799,14 +806,17 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
       YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
     } else if (path == PATH_DIRECT) {
       const bool u8 = e->cur_input_dtype == YB_U8 && op.in.buf == -2;
-      const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(op.in.w) * 2;
+      const bool pool = op.out_mode == OUT_POOL2;               // the 2x2 max pool behind the conv is applied in registers
+      const int rows_per_block = pool ? 2 * FIRST_ROWS : FIRST_ROWS;
+      const int smem_first = (rows_per_block + 2) * FIRST_ROW_ELEMS(op.in.w) * 2;
       const bool mma_ok = op.ksize == 3 && op.cin == 3 && op.stride == 1 && op.cout % 32 == 0 && !op.out.f32 && !op.has_res &&
-                          op.out_mode == OUT_PLAIN && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
+                          (op.out_mode == OUT_PLAIN || pool) && op.out.ld % 8 == 0 && op.out.coff % 8 == 0 && e->conv_impl == 0 &&
                           op.in.ld == 3 && (op.in.w * 3) % 4 == 0 && smem_first <= 200 * 1024;
+      if (pool && !mma_ok) return fail(YB_ERR_INVALID, "layer %d: the fused conv + max-pool needs the tensor-core first-conv kernel", op.layer);
       if (mma_ok) {
-        const int groups = n * ceil_div(op.Ho, FIRST_ROWS);     // stride 1: output rows == input rows
+        const int groups = n * ceil_div(op.Ho, rows_per_block);     // stride 1: output rows == input rows
         auto launch = [&](auto kern) -> int {
-          const int res = e->first_resident[u8 ? 1 : 0];          // co-resident blocks per SM (set_kernel_attrs)
+          const int res = e->first_resident[(pool ? 2 : 0) + (u8 ? 1 : 0)];          // co-resident blocks per SM (set_kernel_attrs)
           // exactly one resident wave: the blocks walk the row groups with a grid stride, a partial second wave
           // would run at a fraction of the occupancy
           dim3 grid(std::min(groups, e->num_sms * res / std::max(1, op.cout / 32)), op.cout / 32);
@@ -815,8 +825,9 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
           YB_CUDA(cudaGetLastError());
           return YB_OK;
         };
-        if (u8) return launch(conv_first_mma_kernel<true>);
-        return launch(conv_first_mma_kernel<false>);
+        if (pool) return u8 ? launch(conv_first_mma_kernel<true, true>) : launch(conv_first_mma_kernel<false, true>);
+        if (u8) return launch(conv_first_mma_kernel<true, false>);
+        return launch(conv_first_mma_kernel<false, false>);
       }
       const int smem = a.taps * op.cin * 32 * 4;
       dim3 grid(ceil_div(a.M, 128), ceil_div(op.cout, 32));
@@ -942,6 +953,11 @@ static int compile_plan(yb_engine* e) {
     // indistinguishable (14,885 vs 14,904 img/s), so the variant with two launches less stays the default.
     else if (e->fuse_upsample && P[j].kind == YB_UPSAMPLE && P[j].stride == 2) { absorbed_into[i] = j; out_mode[i] = OUT_UPSAMPLE2; }
     else if (P[j].kind == YB_REORG && P[j].stride == 2 && (e->shape[i].h % 2 == 0) && (e->shape[i].w % 2 == 0)) { absorbed_into[i] = j; out_mode[i] = OUT_REORG2; }
+    // Darknet-19's first conv + max pool (net/v2.py:20-22): pooled in the registers of the tensor-core first-conv kernel
+    else if (P[j].kind == YB_MAXPOOL && P[P[i].src[0]].kind == YB_INPUT && e->C == 3 && P[i].ksize == 3 && P[i].stride == 1 &&
+             P[i].filters % 32 == 0 && P[i].batch_norm && e->shape[i].h % 2 == 0 && e->shape[i].w % 2 == 0 && (e->W * 3) % 4 == 0 &&
+             (2 * FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2 <= 200 * 1024 &&
+             (e->fuse_pool == 2 || (e->fuse_pool == 1 && !e->keep_all))) { absorbed_into[i] = j; out_mode[i] = OUT_POOL2; }
   }
   std::vector<bool> absorbs(n, false);
   for (int i = 0; i < n; ++i) if (absorbed_into[i] >= 0) absorbs[absorbed_into[i]] = true;
@@ -1084,7 +1100,7 @@ static int compile_plan(yb_engine* e) {
       }
       op.cout_pad = round_up(op.cout, (op.path == PATH_TC || op.path == PATH_FUSED) ? op.bn_max : 4);
       emit = true;
-    } else if (l.kind == YB_MAXPOOL) {
+    } else if (l.kind == YB_MAXPOOL && !absorbs[i]) {
       op.kind = OP_MAXPOOL; op.in = e->view[l.src[0]]; op.out = e->view[i]; emit = true;
       if (op.in.f32 || op.in.buf < 0) return fail(YB_ERR_INVALID, "layer %d: max pool needs a bf16 activation input", i);
     } else if (l.kind == YB_SHORTCUT && !absorbs[i]) {
@@ -1449,6 +1465,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   if (fs) e->fuse_stem = atoi(fs);
   const char* fb = getenv("YB_FUSE_BLOCK");
   if (fb) e->fuse_block = atoi(fb);
+  const char* fp = getenv("YB_FUSE_POOL");
+  if (fp) e->fuse_pool = atoi(fp);
   const char* pp = getenv("YB_PIXEL_PAIRS");
   if (pp) e->pixel_pairs = atoi(pp);
   const char* pd = getenv("YB_PDL");
