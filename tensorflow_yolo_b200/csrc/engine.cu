@@ -170,6 +170,7 @@ struct PostCtx {
   float4 *sorted_f4 = nullptr, *sorted_f4s = nullptr, *sorted_f4i = nullptr, *sorted_ky = nullptr, *sorted_kx = nullptr;
   float2* sorted_area = nullptr;
   int* sorted_cls = nullptr;
+  unsigned long long* sorted_qidx = nullptr;
   unsigned char* flags = nullptr;
   int *order = nullptr, *n_keep = nullptr, *n_cand = nullptr;
   DetOut* dets = nullptr;
@@ -194,6 +195,7 @@ struct PostCtx {
     YB_CUDA(cudaMalloc(&sorted_f4i, nr * sizeof(float4)));
     YB_CUDA(cudaMalloc(&sorted_area, nr * sizeof(float2)));
     YB_CUDA(cudaMalloc(&sorted_cls, nr * 4)); YB_CUDA(cudaMalloc(&flags, nr));
+    YB_CUDA(cudaMalloc(&sorted_qidx, nr * 8));
     YB_CUDA(cudaMalloc(&order, nr * 4));
     YB_CUDA(cudaMalloc(&n_keep, (size_t)max_batch * 4)); YB_CUDA(cudaMalloc(&n_cand, (size_t)max_batch * 4));
     dets_cap = 0;
@@ -202,7 +204,7 @@ struct PostCtx {
   }
   void release() {
     cudaFree(prob); cudaFree(x); cudaFree(y); cudaFree(w); cudaFree(h); cudaFree(cls); cudaFree(keys);
-    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4s); cudaFree(sorted_ky); cudaFree(sorted_kx); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
+    cudaFree(sorted_boxes); cudaFree(sorted_f4); cudaFree(sorted_f4s); cudaFree(sorted_ky); cudaFree(sorted_kx); cudaFree(sorted_f4i); cudaFree(sorted_area); cudaFree(sorted_cls); cudaFree(sorted_qidx); cudaFree(flags); cudaFree(order); cudaFree(n_keep); cudaFree(n_cand);
     cudaFree(dets);
     for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
   }
@@ -259,7 +261,7 @@ struct PostCtx {
     a.rows = rows; a.per_class = per_class; a.thr = thr;
     { const char* dbg = getenv("YB_NMS_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     a.prob = prob; a.x = x; a.y = y; a.w = w; a.h = h; a.cls = cls;
-    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_ky = sorted_ky; a.sorted_kx = sorted_kx; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls;
+    a.keys = keys; a.rows_pow2 = rows_pow2; a.sorted_boxes = sorted_boxes; a.sorted_f4 = sorted_f4; a.sorted_f4s = sorted_f4s; a.sorted_ky = sorted_ky; a.sorted_kx = sorted_kx; a.sorted_f4i = sorted_f4i; a.sorted_area = sorted_area; a.sorted_cls = sorted_cls; a.sorted_qidx = sorted_qidx;
     a.flags = flags; a.order = order; a.n_keep = n_keep; a.n_cand = n_cand;
     return a;
   }

@@ -566,6 +566,8 @@ struct NmsArgs {
   float4* sorted_f4i;   // [n * rows]: inward-rounded float corners          } float interval arithmetic,
   float2* sorted_area;  // [n * rows]: area rounded down / up to float       } see decide_f32
   int* sorted_cls;      // [n * rows]
+  unsigned long long* sorted_qidx;   // [n * rows]: the eight bucket indices (one byte each) of a box's lookup values in the
+                                     // image-wide direct-address tables of the pipelined sweep
   unsigned char* flags; // [n * rows] bit0: removed, bit1: kept, bit2: non-finite or irregular box (exact path only)
   // outputs
   int* order;           // [n * rows]: kept rows in kept order
@@ -696,6 +698,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   __shared__ int s_scan[32];
   __shared__ int s_next[2];                    // next group of 32 later boxes of the sweep (per kept-block buffer)
   __shared__ int s_running;
+  // image-wide span of the finite prefilter keys per condition (orderable encoding), then the bucket function
+  // b(v) = floor((v - s_qlo) * s_qsc) shared by every block's direct-address tables
+  __shared__ unsigned s_glo[8], s_ghi[8];
+  __shared__ float s_qlo[8], s_qsc[8];
 
   const int img = blockIdx.x;
   const int R = a.rows;
@@ -707,6 +713,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   // (orderable score << 32) | (0xFFFFFFFF - row); then sort descending ----
   unsigned long long* gkeys = a.keys + (long long)img * a.rows_pow2;     // only dereferenced beyond NMS_SMEM_KEYS candidates
   if (tid == 0) s_count = 0;
+  if (tid < 8) { s_glo[tid] = 0xFFFFFFFFu; s_ghi[tid] = 0u; }
   __syncthreads();
   for (int r0 = 0; r0 < R; r0 += 4 * NMS_THREADS) {
     float pr4[4];                                  // four independent loads in flight before the (ordered) atomics
@@ -717,11 +724,21 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (pr4[u] == pr4[u]) {
-        const int r = r0 + u * NMS_THREADS + tid;
-        const int pos = atomicAdd(&s_count, 1);
-        const unsigned long long key = ((unsigned long long)orderable(pr4[u]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)r);
-        if (pos < NMS_SMEM_KEYS) s_keys[pos] = key; else gkeys[pos] = key;
+      // warp-aggregated compaction: one ballot, one shared-memory atomic per warp, the lanes take consecutive slots
+      // (the order of the keys does not matter: they are sorted next)
+      const bool is_cand = pr4[u] == pr4[u];
+      const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
+      if (ballot) {
+        const int lane = tid & 31;
+        int slot0 = 0;
+        if (lane == __ffs(ballot) - 1) slot0 = atomicAdd(&s_count, __popc(ballot));
+        slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(ballot) - 1);
+        if (is_cand) {
+          const int r = r0 + u * NMS_THREADS + tid;
+          const int pos = slot0 + __popc(ballot & ((1u << lane) - 1u));
+          const unsigned long long key = ((unsigned long long)orderable(pr4[u]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)r);
+          if (pos < NMS_SMEM_KEYS) s_keys[pos] = key; else gkeys[pos] = key;
+        }
       }
     }
   }
@@ -765,6 +782,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
   int* scls = a.sorted_cls + base;
   unsigned char* flags = a.flags + base;
   int* order = a.order + base;
+  unsigned long long* sqidx = a.sorted_qidx + base;
+  const bool tables = use_f32 && K > NMS_BLOCK;          // the pipelined sweep below (the only user of the bucket tables)
+  float span_lo[8], span_hi[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { span_lo[c] = INFINITY; span_hi[c] = -INFINITY; }
   for (int i = tid; i < K; i += NMS_THREADS) {
     const unsigned long long key = in_smem ? s_keys[i] : gkeys[i];
     const int r = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
@@ -788,6 +810,51 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
     skx[i] = make_float4(bf.out.x, bf.out.z, shr.x, shr.z);
     flags[i] = exact_only ? 4 : 0;
     order[i] = r;          // provisional: sorted row ids; compacted to kept rows in step 5
+    if (tables && !exact_only) {
+      // the keys this box contributes to the sorted tables of its block (prepare_block), in condition order
+      const float kc8[8] = {shr.z, shr.x, bf.out.z, bf.out.x, shr.w, shr.y, bf.out.w, bf.out.y};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (kc8[c] > -INFINITY && kc8[c] < INFINITY) { span_lo[c] = fminf(span_lo[c], kc8[c]); span_hi[c] = fmaxf(span_hi[c], kc8[c]); }
+      }
+    }
+  }
+  if (tables) {
+    // image-wide bucket function: one span per condition over all finite keys; every box's eight bucket indices are
+    // computed once here instead of once per (box, block) in the sweep
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float lo = span_lo[c], hi = span_hi[c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+      }
+      if ((tid & 31) == 0 && lo <= hi) { atomicMin(&s_glo[c], orderable(lo)); atomicMax(&s_ghi[c], orderable(hi)); }
+    }
+    __syncthreads();
+    if (tid < 8) {
+      float lo = 0.f, sc = 0.f;
+      if (s_glo[tid] <= s_ghi[tid]) {
+        lo = unorderable(s_glo[tid]);
+        const float span = __fsub_rn(unorderable(s_ghi[tid]), lo);
+        sc = (span > 0.f && span < INFINITY) ? __fdiv_rn((float)NMS_QB, span) : 0.f;
+        if (!(sc < INFINITY)) sc = 0.f;
+      }
+      s_qlo[tid] = lo; s_qsc[tid] = sc;
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += NMS_THREADS) {
+      const float4 vx = skx[i], vy = sky[i];
+      const float v8[8] = {vx.x, vx.y, vx.z, vx.w, vy.x, vy.y, vy.z, vy.w};
+      unsigned long long packed = 0ull;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const unsigned b = min(__float2uint_rd(__fmul_rn(__fsub_rn(v8[c], s_qlo[c]), s_qsc[c])), (unsigned)(NMS_QB - 1));
+        packed |= (unsigned long long)b << (8 * c);
+      }
+      sqidx[i] = packed;
+    }
   }
   __syncthreads();
 
@@ -1013,13 +1080,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         const int n_neg = __popc(__ballot_sync(0xffffffffu, k0 == -INFINITY)) + __popc(__ballot_sync(0xffffffffu, k1 == -INFINITY));
         const int n_pos = __popc(__ballot_sync(0xffffffffu, k0 == INFINITY)) + __popc(__ballot_sync(0xffffffffu, k1 == INFINITY));
         __syncwarp();
-        if (lane == 0) {
-          float lo = 0.f, hi = 0.f;
-          if (n_neg + n_pos < NMS_BLOCK) { lo = blk.skey[cnd][n_neg]; hi = blk.skey[cnd][NMS_BLOCK - 1 - n_pos]; }
-          const float span = __fsub_rn(hi, lo);
-          const float sc = (span > 0.f && span < INFINITY) ? __fdiv_rn((float)NMS_QB, span) : 0.f;
-          reinterpret_cast<float*>(blk.qlo)[cnd] = lo;
-          reinterpret_cast<float*>(blk.qscale)[cnd] = (sc < INFINITY) ? sc : 0.f;
+        (void)n_neg; (void)n_pos;
+        if (lane == 0) {       // the image-wide bucket function (the boxes of a block are spread over the whole image anyway)
+          reinterpret_cast<float*>(blk.qlo)[cnd] = s_qlo[cnd];
+          reinterpret_cast<float*>(blk.qscale)[cnd] = s_qsc[cnd];
         }
       }
       nms_preparer_barrier();
@@ -1138,20 +1202,23 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) sort_nms_kernel(const NmsArgs 
         int g = grab();
         int j0 = first + g * 32;
         unsigned char fj_n = (unsigned char)1;
-        float4 vx_n = make_float4(0.f, 0.f, 0.f, 0.f), vy_n = vx_n;
-        if (j0 + lane < K) { fj_n = flags[j0 + lane]; vx_n = skx[j0 + lane]; vy_n = sky[j0 + lane]; }
+        unsigned long long qi_n = 0ull;
+        if (j0 + lane < K) { fj_n = flags[j0 + lane]; qi_n = sqidx[j0 + lane]; }
         while (j0 < K) {
           const int j = j0 + lane;
           const unsigned char fj = fj_n;
-          const float4 vxj = vx_n, vyj = vy_n;
+          const unsigned long long qi = qi_n;
           g = grab();
           j0 = first + g * 32;
           fj_n = (unsigned char)1;
-          if (j0 + lane < K) { fj_n = flags[j0 + lane]; vx_n = skx[j0 + lane]; vy_n = sky[j0 + lane]; }
+          if (j0 + lane < K) { fj_n = flags[j0 + lane]; qi_n = sqidx[j0 + lane]; }
           const bool live = !(fj & 1);
           unsigned long long todo = 0ull;
           if (live && !(fj & 4)) {
-            todo = bucket_candidates(kc, vxj, vyj) & kept_c;
+            // eight direct-address lookups with the box's precomputed bucket indices: a superset of candidates()
+            const unsigned qa = (unsigned)qi, qb = (unsigned)(qi >> 32);
+            todo = kc.qmask[0][qa & 0xFFu] & kc.qmask[1][(qa >> 8) & 0xFFu] & kc.qmask[2][(qa >> 16) & 0xFFu] & kc.qmask[3][qa >> 24] &
+                   kc.qmask[4][qb & 0xFFu] & kc.qmask[5][(qb >> 8) & 0xFFu] & kc.qmask[6][(qb >> 16) & 0xFFu] & kc.qmask[7][qb >> 24] & kept_c;
           } else if (live) {
             // an exact-only box j (rare): numpy-semantics IoU against every kept box, on this lane alone
             const BoxC<T> bj = sb[j];
