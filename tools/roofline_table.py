@@ -23,19 +23,29 @@ def main():
         peaks.update({k: v for k, v in json.load(open(pk)).items() if k in peaks})
     B = d["batch"]
     g = defaultdict(lambda: {"n": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0, "cfg": None})
-    for o in d["ops"]:
-        if o["kind"] != "conv":
-            continue
+    ops = [o for o in d["ops"] if o["kind"] == "conv"]
+    for n_op, o in enumerate(ops):
         h, w, c = o["out_hwc"]
         k, s, cin = o["ksize"], o["stride"], o["cin"]
-        key = (h, w, c, k, s, cin)
+        if o["path"] != 3 and o["ms"] < 2e-2 and n_op + 1 < len(ops) and ops[n_op + 1]["path"] == 3:
+            continue                                     # the producer of a fused pair: accounted for on the consumer's row
+        key = (h, w, c, k, s, cin, o["path"])
         e = g[key]
         e["n"] += 1
         e["ms"] += o["ms"]
         e["flop"] += 2.0 * B * h * w * c * k * k * cin
         out_b = 4 if (c % 85 == 0 and k == 1) else 2          # the heads are written in fp32
         e["bytes"] += B * (h * s * w * s * cin * (2 if cin > 3 else 4) + h * w * c * out_b) + c * k * k * cin * 2
-        e["cfg"] = "BN{} BK{}{}{}".format(o["bn"], o["bk"], " pair" if o.get("pair") else "", " ksub?" if False else "") if o["path"] == 0 else "mma.sync"
+        if o["path"] == 3:
+            # fused pair (conv_fused.cuh): + the producer's FLOPs; bytes = the producer's input + this output (+ nothing for the
+            # residual: it is the producer's input, read once), the intermediate never reaches HBM
+            p = ops[n_op - 1]
+            ph, pw, pc = p["out_hwc"]
+            e["flop"] += 2.0 * B * ph * pw * pc * p["ksize"] * p["ksize"] * p["cin"]
+            e["bytes"] += B * (ph * pw * p["cin"] * (2 if p["cin"] > 3 else 4)) - B * (h * s * w * s * cin * 2)
+            e["cfg"] = "fused pair: {}x{} {}->{} + this (mma.sync producer, tcgen05 BN64 BK32)".format(p["ksize"], p["ksize"], p["cin"], pc)
+        else:
+            e["cfg"] = "BN{} BK{}{}".format(o["bn"], o["bk"], " pair" if o.get("pair") else "") if o["path"] == 0 else "mma.sync"
     tot_ms = sum(e["ms"] for e in g.values())
     print("# Per-layer-class roofline, YOLOv3-416 batch {} on one B200".format(B))
     print()
@@ -47,7 +57,7 @@ def main():
     print("|---|---|---|---|---|---|---|---|")
     tot_floor = 0.0
     for key, e in sorted(g.items(), key=lambda kv: -kv[1]["ms"]):
-        h, w, c, k, s, cin = key
+        h, w, c, k, s, cin, _path = key
         t_tc = e["flop"] / (peaks["bf16_tflops"] * 1e12) * 1e3
         t_hbm = e["bytes"] / (peaks["hbm_gbs"] * 1e9) * 1e3
         floor = max(t_tc, t_hbm)
