@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <thread>
 #include <vector>
@@ -344,8 +345,11 @@ struct Op {
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
   __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
+  std::vector<float> h_scale, h_shift;      // host copies (the fused kernels take the consumer's BN by value)
   alignas(64) CUtensorMap tmA, tmOut, tmRes;
-  alignas(64) CUtensorMap tmOut4, tmRes4;   // fused ops: output / residual as (C, W, H, N), box 64 x 16 x 2 x 1
+  alignas(64) CUtensorMap tmOut4;           // fused ops: output as (C, W, H, N), box 64 x 16 x 2 x 1
+  alignas(64) CUtensorMap tmIn4;            // fused block: producer input (= residual) as (C, W, H, N), box 64 x 18 x 10 x 1
+  alignas(64) CUtensorMap tmW1;             // fused block: the 1x1 producer's weights [32][64], one box
   alignas(64) CUtensorMap tmB[4];           // weight maps with box rows 32, 64, 128, 256 (128 doubles as the pair half)
   bool tma_epi = false;
   // generic
@@ -556,6 +560,8 @@ struct yb_engine {
   std::vector<cudaEvent_t> prof_events;      // (n_ops + 1) per profiled forward
   const void* cur_input = nullptr;
   int cur_input_dtype = YB_F32;
+  struct StemMap { const void* ptr; int dtype; alignas(64) CUtensorMap map; };
+  std::deque<StemMap> stem_maps;            // launch_fused: input tensor maps per (address, element type); deque: stable addresses
   float* d_u8_lut = nullptr;
   float* scratch_f32 = nullptr;   // read_output / read_layer staging
   size_t scratch_floats = 0;
@@ -725,14 +731,39 @@ static std::vector<ConvCfg> candidate_cfgs(const Op& op, int n, bool allow_pair)
   return v;
 }
 
+// The fused stem reads the network input through a 3-D tiled tensor map over (W*3 elements, H, N): one per input
+// address and element type (the two staging slots, or whatever device pointer the caller passes), cached.
+static int stem_input_map(yb_engine* e, const void* ptr, int dtype, const CUtensorMap** out) {
+  for (auto& c : e->stem_maps) if (c.ptr == ptr && c.dtype == dtype) { *out = &c.map; return YB_OK; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0)
+    return fail(YB_ERR_INVALID, "the fused first layers read the input by TMA: a device input must be 16-byte aligned (or set YB_FUSE_STEM=0)");
+  const size_t es = dtype == YB_U8 ? 1 : 4;
+  if (e->stem_maps.size() >= 64) e->stem_maps.clear();          // callers cycling through many device buffers
+  e->stem_maps.emplace_back();
+  auto& c = e->stem_maps.back();
+  c.ptr = ptr; c.dtype = dtype;
+  cuuint64_t dims[3] = {(cuuint64_t)e->W * 3, (cuuint64_t)e->H, (cuuint64_t)e->max_batch};
+  cuuint64_t strides[2] = {(cuuint64_t)e->W * 3 * es, (cuuint64_t)e->H * e->W * 3 * es};
+  cuuint32_t box[3] = {(cuuint32_t)(dtype == YB_U8 ? STEM_RAW_ROW_U8 : STEM_PATCH_PITCH), (cuuint32_t)STEM_PATCH_ROWS, 1};
+  cuuint32_t est[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(&c.map, dtype == YB_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
+                              dims, strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e->stem_maps.pop_back(); return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(network input) failed (%d)", (int)r); }
+  *out = &c.map;
+  return YB_OK;
+}
+
 // conv_fused.cuh: one persistent CTA per SM over 8 x 16 output tiles
 static int launch_fused(yb_engine* e, Op& op, int n) {
   const Op& pp = e->ops[op.fuse_src];
   FuseArgs a;
   memset(&a, 0, sizeof(a));
   a.n_img = n; a.Ho = op.Ho; a.Wo = op.Wo; a.H = pp.in.h; a.W = pp.in.w;
-  a.in = view_ptr(e, pp.in); a.in_ld = pp.in.ld;
-  a.scale1 = pp.d_scale; a.shift1 = pp.d_shift; a.scale2 = op.d_scale; a.shift2 = op.d_shift;
+  a.scale1 = pp.d_scale; a.shift1 = pp.d_shift;
+  if ((int)op.h_scale.size() < FUSE_COUT || (int)op.h_shift.size() < FUSE_COUT) return fail(YB_ERR_STATE, "layer %d: fused conv launched before its weights were loaded", op.layer);
+  memcpy(a.scale2, op.h_scale.data(), sizeof(a.scale2));
+  memcpy(a.shift2, op.h_shift.data(), sizeof(a.shift2));
   a.leaky1 = pp.leaky; a.leaky2 = op.leaky;
   a.tiles_h = op.Ho / FUSE_TH; a.tiles_w = op.Wo / FUSE_TW; a.n_tiles = n * a.tiles_h * a.tiles_w;
   a.dbg = e->dbg_counters;
@@ -740,11 +771,17 @@ static int launch_fused(yb_engine* e, Op& op, int n) {
   const CUtensorMap& tmB = op.tmB[bn_index(FUSE_COUT)];
   if (op.fuse_kind == FUSE_STEM) {
     a.w1 = pp.d_wt32;
-    if (e->cur_input_dtype == YB_U8) stem_fused_kernel<true><<<grid, FUSE_THREADS, FUSE_SMEM_STEM, e->stream>>>(tmB, op.tmOut4, a);
-    else stem_fused_kernel<false><<<grid, FUSE_THREADS, FUSE_SMEM_STEM, e->stream>>>(tmB, op.tmOut4, a);
+    const CUtensorMap* tmIn = nullptr;
+    YB_TRY(stem_input_map(e, e->cur_input, e->cur_input_dtype, &tmIn));
+    if (e->cur_input_dtype == YB_U8) stem_fused_kernel<true><<<grid, FUSE_THREADS, fuse_smem_stem<true>(), e->stream>>>(*tmIn, tmB, op.tmOut4, a);
+    else stem_fused_kernel<false><<<grid, FUSE_THREADS, fuse_smem_stem<false>(), e->stream>>>(*tmIn, tmB, op.tmOut4, a);
   } else {
-    a.w1 = pp.d_wt;
-    block_fused_kernel<<<grid, FUSE_THREADS, FUSE_SMEM_BLOCK, e->stream>>>(tmB, op.tmOut4, op.tmRes4, a);
+    BlockArgs ba;
+    ba.f = a;
+    if ((int)pp.h_scale.size() < FUSE_CMID || (int)pp.h_shift.size() < FUSE_CMID) return fail(YB_ERR_STATE, "layer %d: fused conv launched before its weights were loaded", pp.layer);
+    memcpy(ba.scale1, pp.h_scale.data(), sizeof(ba.scale1));
+    memcpy(ba.shift1, pp.h_shift.data(), sizeof(ba.shift1));
+    block_fused_kernel<<<grid, BLK_THREADS, FUSE_SMEM_BLOCK, e->stream>>>(op.tmIn4, op.tmW1, tmB, op.tmOut4, ba);
   }
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -763,8 +800,8 @@ static int set_kernel_attrs(yb_engine* e) {
   YB_TRY((set_tcp_attr<256, 64, false>())); YB_TRY((set_tcp_attr<128, 64, false>())); YB_TRY((set_tcp_attr<64, 64, false>()));
   YB_TRY((set_tcp_attr<32, 64, false>())); YB_TRY((set_tcp_attr<128, 32, false>())); YB_TRY((set_tcp_attr<64, 32, false>()));
   YB_TRY((set_tcp_attr<32, 32, false>()));
-  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
-  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_STEM));
+  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_smem_stem<true>()));
+  YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_smem_stem<false>()));
   YB_CUDA(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_BLOCK));
   const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2, smem_pool = (2 * FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2;
   if (smem_first <= 200 * 1024) {
@@ -1196,13 +1233,17 @@ static int build_tensor_maps(yb_engine* e) {
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D output) failed (%d) for layer %d", (int)r, op.layer);
-      memset(&op.tmRes4, 0, sizeof(op.tmRes4));
-      if (op.fuse_kind == FUSE_BLOCK) {       // the residual is the producer's input tensor
-        cuuint64_t rstrides[3] = {(cuuint64_t)op.in2.ld * 2, (cuuint64_t)op.Wo * op.in2.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.in2.ld * 2};
-        r = g_encode_tiled(&op.tmRes4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.in2), dims, rstrides, box, es,
+      memset(&op.tmIn4, 0, sizeof(op.tmIn4));
+      if (op.fuse_kind == FUSE_BLOCK) {       // the producer's input patch (its centre is the residual): 10 x 18 pixels x 64 channels
+        cuuint64_t idims[4] = {64, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
+        cuuint64_t istrides[3] = {(cuuint64_t)op.in2.ld * 2, (cuuint64_t)op.Wo * op.in2.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.in2.ld * 2};
+        cuuint32_t ibox[4] = {64, (cuuint32_t)BLOCK_PATCH_W, (cuuint32_t)BLOCK_PATCH_H, 1};
+        r = g_encode_tiled(&op.tmIn4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.in2), idims, istrides, ibox, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D residual) failed (%d) for layer %d", (int)r, op.layer);
+        if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D block input) failed (%d) for layer %d", (int)r, op.layer);
+        const Op& pp = e->ops[op.fuse_src];
+        YB_TRY(make_tiled_map(&op.tmW1, pp.d_wt, pp.cout_pad, 64, 64, FUSE_CMID, 64));
       }
       continue;
     }
@@ -1635,6 +1676,7 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
     YB_CUDA(cudaMalloc(&op.d_shift, (size_t)op.cout_pad * 4));
     YB_CUDA(cudaMemcpy(op.d_scale, scale.data(), (size_t)op.cout_pad * 4, cudaMemcpyHostToDevice));
     YB_CUDA(cudaMemcpy(op.d_shift, shift.data(), (size_t)op.cout_pad * 4, cudaMemcpyHostToDevice));
+    op.h_scale = scale; op.h_shift = shift;
   }
   if (consumed) *consumed = read;
   YB_TRY(build_tensor_maps(e));
