@@ -194,7 +194,11 @@ int yb_engine_tune_report(yb_engine* e, char* buf, size_t capacity, size_t* need
  * 1 = no epilogue work, 2 = no MMAs, 4 = no activation loads, 8 = no weight loads; outputs are wrong while set),
  * "graph" (CUDA graph of the forward: -1 = automatic, used for batches of at most 32 images, where the 75 launches
  * rather than the device work bound sess.run of net/yolo.py:83; 0 = never; 1 = always.  A (batch, input buffer, dtype)
- * combination runs eagerly the first time, is captured the second time and replayed from then on). */
+ * combination runs eagerly the first time, is captured the second time and replayed from then on),
+ * "split_k" (latency mode, default 0 or YB_SPLIT_K: convs whose grid fills a fraction of the SMs -- small batches, the
+ * per-GPU shards of a strong-scaled batch, config/yolo_3.ini:36 batch_size = 1 -- are split along K over 2-4 work
+ * units per tile, partial accumulators summed in a fixed order; the fp32 summation order, hence the last bits of the
+ * output, then depend on the batch size, which is why it is opt-in). */
 int yb_engine_set_option(yb_engine* e, const char* name, int value);
 /* Forces the launch configuration of launched op `op_index` (bn = 0 restores the heuristic; bstat / tma_epi: -1 =
  * heuristic, 0 = off, 1 = on when possible; ksub = BK-blocks per pipeline stage, 0 = heuristic) and times one op in isolation (average of reps launches, milliseconds). */
@@ -233,6 +237,8 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
 /* Launch configuration of op `op_index` as resolved by its last launch: N tile, CTA pairs, weight-stationary B,
  * TMA-store epilogue, pipeline stages, BK-blocks per stage. */
 int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat, int* tma_epi, int* stages, int* ksub);
+/* Split-K factor the last launch of op `op_index` used (1 = none; option "split_k"). */
+int yb_engine_op_splitk(yb_engine* e, int op_index, int* splitk);
 
 /* ---- stand-alone post-processing on caller tensors ---- */
 typedef struct yb_scale {

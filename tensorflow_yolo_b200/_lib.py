@@ -86,6 +86,7 @@ _SIGNATURES = {
     "yb_engine_op_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_int),
                                          _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_double)]),
     "yb_engine_op_cfg": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int] + [_P(ctypes.c_int)] * 6),
+    "yb_engine_op_splitk": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int)]),
     "yb_post_create": (ctypes.c_int, [_P(yb_scale), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, _P(ctypes.c_void_p)]),
     "yb_post_destroy": (None, [ctypes.c_void_p]),

@@ -290,6 +290,13 @@ struct PersistArgs {
   int solo_issue;      // 1: a single thread runs the MMA issue loop; 0: the whole warp walks it, electing per stage
   int ablate;          // debug/roofline probes (results are wrong when non-zero): 1 = epilogue does nothing,
                        // 2 = no MMAs, 4 = no A loads, 8 = no B loads
+  int splitk;          // > 1: every tile is computed by `splitk` work units (consecutive units = the parts of one tile, so
+                       // they run on neighbouring CTAs at the same time), each walking num_k / splitk K blocks; the raw
+                       // fp32 accumulators go to `ws`, the last part to arrive (per epilogue warp, counted in `ws_cnt`)
+                       // sums all parts in part order -- deterministic -- and runs the epilogue.  Latency mode for grids
+                       // that fill a fraction of the SMs (small batches): fp32 summation order differs from splitk = 1.
+  float* ws;           // [n_tiles * splitk][pair rank][128][BN] partial accumulators
+  unsigned int* ws_cnt;// [n_tiles][pair rank][8 epilogue warps] arrival counters (zero between launches: the last part resets them)
   unsigned long long* dbg;   // optional [16] cycle counters summed over all CTAs (see CONV_DBG_*); nullptr = off
 };
 // cycle counters: who waits on whom inside the persistent conv kernel
@@ -306,7 +313,8 @@ __device__ __forceinline__ long long clk() { return clock64(); }
 // ~120 cycles whatever its shape, which is what bounds the narrow-N layers.  The leader (rank 0) issues the MMAs, both
 // CTAs' TMA loads complete on the leader's full barriers, the leader's commits release the smem stages / publish the
 // accumulators in both CTAs, and both CTAs' epilogue warps hand the accumulator back on the leader's tmem_empty barrier.
-template <int BN, int BK, bool PAIR>
+// SPLIT = true: the split-K instantiation (PersistArgs::splitk > 1 allowed); the plain one carries none of its code.
+template <int BN, int BK, bool PAIR, bool SPLIT = false>
 __global__ void __launch_bounds__(CONV_TCP_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a,
@@ -378,6 +386,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // tile walk: single CTA -> tiles blockIdx.x, +gridDim.x, ...; pair -> pair-tiles (cluster id), M tile = 2j + rank
   const int walk_start = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int walk_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // split-K: work unit = (tile, part); num_k is a multiple of splitk (engine.cu: launch_conv_tcp)
+  const int splitk = (SPLIT && pa.splitk > 1) ? pa.splitk : 1;
+  const int n_units = pa.n_tiles * splitk;
+  const int k_per = num_k / splitk;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -407,7 +419,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // latency bounds the TMA issue rate, so the common cases are kept free of the runtime inner loop.
       auto produce = [&](auto ks_tag) {
         constexpr int KS = decltype(ks_tag)::value;
-      for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step) {
+      for (int unit = walk_start; unit < n_units; unit += walk_step) {
+          const int tile = splitk > 1 ? unit / splitk : unit;
+          const int kb_lo = splitk > 1 ? (unit - tile * splitk) * k_per : 0, kb_hi = kb_lo + k_per;
           const int tile_mj = tile / pa.n_tiles_n;
           const int tile_m = PAIR ? 2 * tile_mj + (int)rank : tile_mj;
           const int n0 = (tile - tile_mj * pa.n_tiles_n) * BN;
@@ -421,8 +435,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             base_h = p0 * a.conv_stride - a.pad;
           }
           int cb = 0, kh = 0, kw = 0;
-          for (int kb0 = 0; kb0 < num_k; kb0 += (KS ? KS : ksub)) {
-            const int cnt = KS ? KS : ((num_k - kb0 < ksub) ? num_k - kb0 : ksub);      // BK-blocks in this stage
+          if (kb_lo) {                                 // this part starts inside the K walk: (tap, channel block) of K block kb_lo
+            const int tap = kb_lo / a.kc_blocks;
+            cb = kb_lo - tap * a.kc_blocks;
+            kh = tap / a.kw; kw = tap - kh * a.kw;
+          }
+          for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += (KS ? KS : ksub)) {
+            const int cnt = KS ? KS : ((kb_hi - kb0 < ksub) ? kb_hi - kb0 : ksub);      // BK-blocks in this stage
             const long long t0 = dbg ? clk() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (dbg) t_wait += clk() - t0;
@@ -457,9 +476,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       };
       if (ksub == 1) produce(std::integral_constant<int, 1>{});
-      else if (ksub == 2 && num_k % 2 == 0) produce(std::integral_constant<int, 2>{});
-      else if (ksub == 3 && num_k % 3 == 0) produce(std::integral_constant<int, 3>{});
-      else if (ksub == 9 && num_k % 9 == 0) produce(std::integral_constant<int, 9>{});
+      else if (ksub == 2 && k_per % 2 == 0) produce(std::integral_constant<int, 2>{});
+      else if (ksub == 3 && k_per % 3 == 0) produce(std::integral_constant<int, 3>{});
+      else if (ksub == 9 && k_per % 9 == 0) produce(std::integral_constant<int, 9>{});
       else produce(std::integral_constant<int, 0>{});
       if (dbg) {
         atomicAdd(&pa.dbg[CONV_DBG_PROD_WAIT_EMPTY], (unsigned long long)t_wait);
@@ -486,7 +505,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool dbg = pa.dbg != nullptr;
       long long t_full = 0, t_tmem = 0;
       const long long t_begin = dbg ? clk() : 0;
-      for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
+      for (int unit = walk_start; unit < n_units; unit += walk_step, ++it) {
+        const int kb_lo = splitk > 1 ? (unit % splitk) * k_per : 0, kb_hi = kb_lo + k_per;
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         long long t0 = dbg ? clk() : 0;
@@ -494,8 +514,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (dbg) t_tmem += clk() - t0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb0 = 0; kb0 < num_k; kb0 += (KS ? KS : ksub)) {
-          const int cnt = KS ? KS : ((num_k - kb0 < ksub) ? num_k - kb0 : ksub);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += (KS ? KS : ksub)) {
+          const int cnt = KS ? KS : ((kb_hi - kb0 < ksub) ? kb_hi - kb0 : ksub);
           t0 = dbg ? clk() : 0;
           mbar_wait(&full_bar[stage], phase);
           if (dbg) t_full += clk() - t0;
@@ -510,7 +530,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                   // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (>>4) address field
-                  const uint32_t accum = ((kb0 + j) | k) != 0 ? 1u : 0u;
+                  const uint32_t accum = ((kb0 + j - kb_lo) | k) != 0 ? 1u : 0u;
                   if (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
                   else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, accum);
                 }
@@ -518,10 +538,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             if (PAIR) {
               umma_commit_pair(&empty_bar[stage], 3);                          // frees this smem stage in both CTAs
-              if (kb0 + cnt == num_k) umma_commit_pair(&tmem_full_bar[acc], 3);  // accumulator complete
+              if (kb0 + cnt == kb_hi) umma_commit_pair(&tmem_full_bar[acc], 3);  // accumulator complete
             } else {
               umma_commit(&empty_bar[stage]);
-              if (kb0 + cnt == num_k) umma_commit(&tmem_full_bar[acc]);
+              if (kb0 + cnt == kb_hi) umma_commit(&tmem_full_bar[acc]);
             }
           }
           if (!solo) __syncwarp();
@@ -536,9 +556,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     };
     auto issue = [&](const bool solo) {
       if (ksub == 1) issue_loop(solo, std::integral_constant<int, 1>{});
-      else if (ksub == 2 && num_k % 2 == 0) issue_loop(solo, std::integral_constant<int, 2>{});
-      else if (ksub == 3 && num_k % 3 == 0) issue_loop(solo, std::integral_constant<int, 3>{});
-      else if (ksub == 9 && num_k % 9 == 0) issue_loop(solo, std::integral_constant<int, 9>{});
+      else if (ksub == 2 && k_per % 2 == 0) issue_loop(solo, std::integral_constant<int, 2>{});
+      else if (ksub == 3 && k_per % 3 == 0) issue_loop(solo, std::integral_constant<int, 3>{});
+      else if (ksub == 9 && k_per % 9 == 0) issue_loop(solo, std::integral_constant<int, 9>{});
       else issue_loop(solo, std::integral_constant<int, 0>{});
     };
     if (pa.solo_issue) {
@@ -565,7 +585,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool dbg = pa.dbg != nullptr;
     long long t_acc = 0, t_res = 0, t_buf = 0, t_ld = 0, t_math = 0, t_fs = 0;
     const long long t_begin = dbg ? clk() : 0;
-    for (int tile = walk_start; tile < pa.n_tiles; tile += walk_step, ++it) {
+    for (int unit = walk_start; unit < n_units; unit += walk_step, ++it) {
+      const int tile = splitk > 1 ? unit / splitk : unit;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       // a 32-column tile has a single chunk per lane quarter: the two warps of a quarter take alternate tiles
@@ -756,20 +777,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           else r[g] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      if (has_res && ch_begin < ch_end) load_res(ch_begin, rnext);
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int chunk = ch_begin; chunk < ch_end; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
-        uint4 rcur[4];
-        if (has_res) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-          if (chunk + 1 < ch_end) load_res(chunk + 1, rnext);
-        }
-        tmem_ld_wait();
+      // BN + leaky + residual + store of one 32-column chunk of this lane's row
+      auto finish_chunk = [&](int chunk, const uint32_t (&v)[32], const uint4 (&rcur)[4]) {
         const int cbase = n0 + chunk * 32;
         if (valid && cbase < a.cout) {
           float f[32];
@@ -819,6 +828,81 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
         }
+      };
+      if constexpr (SPLIT) {
+        // ---------- split-K: park the raw accumulator, the last part to arrive reduces and finishes ----------
+        constexpr int R = PAIR ? 2 : 1;
+        const int part = unit - tile * splitk;
+        // workspace layout: per (unit, pair rank) 128 x BN floats as [lane quarter][chunk][float4 index g][lane] -- a warp's
+        // store / load of one float4 per lane covers 512 contiguous bytes (lane-per-row addressing would touch 32 lines)
+        const size_t lane_in_unit = ((size_t)rank * 128 * BN) + (size_t)quarter * NCH * 1024 + (size_t)lane * 4;
+        float* wrow = pa.ws + ((size_t)(tile * splitk + part) * R) * 128 * BN + lane_in_unit;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = ch_begin; chunk < ch_end; ++chunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            __stcg(reinterpret_cast<float4*>(wrow + chunk * 1024 + g * 128),
+                   make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(tmem_empty0 + (uint32_t)acc * 8u);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned int* cnt = pa.ws_cnt + ((size_t)tile * R + rank) * CONV_TCP_EPI_WARPS + (warp - 2);
+        unsigned int arrived = 0;
+        if (lane == 0) arrived = atomicAdd(cnt, 1u);
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == (unsigned)(splitk - 1)) {
+          if (lane == 0) *cnt = 0u;                            // ready for the next launch
+          __threadfence();
+          const float* rrow = pa.ws + ((size_t)(tile * splitk) * R) * 128 * BN + lane_in_unit;
+          const size_t part_stride = (size_t)R * 128 * BN;
+#pragma unroll 1
+          for (int chunk = ch_begin; chunk < ch_end; ++chunk) {
+            float sacc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sacc[j] = 0.0f;
+            for (int p = 0; p < splitk; ++p) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(rrow + (size_t)p * part_stride + chunk * 1024 + g * 128));
+                sacc[g * 4] += t.x; sacc[g * 4 + 1] += t.y; sacc[g * 4 + 2] += t.z; sacc[g * 4 + 3] += t.w;
+              }
+            }
+            uint32_t v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sacc[j]);
+            uint4 rcur[4];
+            if (has_res) load_res(chunk, rcur);
+            finish_chunk(chunk, v, rcur);
+          }
+        }
+        continue;
+      }
+      if (has_res && ch_begin < ch_end) load_res(ch_begin, rnext);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = ch_begin; chunk < ch_end; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32), v);
+        uint4 rcur[4];
+        if (has_res) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+          if (chunk + 1 < ch_end) load_res(chunk + 1, rnext);
+        }
+        tmem_ld_wait();
+        finish_chunk(chunk, v, rcur);
       }
       // this warp has finished reading the accumulator: hand it back to the MMA warp
       tc_fence_before();

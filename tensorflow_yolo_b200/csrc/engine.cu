@@ -341,7 +341,7 @@ struct Op {
   int fuse_kind = FUSE_NONE, fuse_src = -1;
   bool skip = false;
   ConvCfg cfg;
-  int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0;   // what the last launch resolved to
+  int launched_stages = 0, launched_bstat = 0, launched_tma_epi = 0, launched_ksub = 0, launched_splitk = 1;   // what the last launch resolved to
   float tuned_ms = 0.f, default_ms = 0.f;                              // autotune: best candidate vs the heuristic
   __nv_bfloat16* d_wt = nullptr;            // [cout_pad][K], cout_pad = round_up(cout, bn_max)
   float *d_wt32 = nullptr, *d_scale = nullptr, *d_shift = nullptr;
@@ -538,6 +538,11 @@ struct yb_engine {
   int solo_issue = 1;           // MMA issue loop run by one thread (1) or by the whole warp electing per stage (0)
   int ablate = 0;               // debug probes of the persistent conv kernel (see PersistArgs::ablate)
   unsigned long long* dbg_counters = nullptr;   // device [CONV_DBG_COUNT] cycle counters while "cycles" is switched on
+  // Split-K latency mode (option "split_k" / YB_SPLIT_K, off by default: it changes the fp32 summation order with the
+  // batch size): partial accumulators of the convs whose grids fill a fraction of the SMs, and their arrival counters
+  int split_k = 0;
+  float* splitk_ws = nullptr; size_t splitk_ws_bytes = 0;
+  unsigned int* splitk_cnt = nullptr; size_t splitk_cnt_n = 0;
   int num_sms = 148;
   std::string tune_report;      // JSON written by yb_engine_autotune
   std::vector<Shape> shape;
@@ -604,11 +609,34 @@ struct LaunchEnv {
   int ablate;
   unsigned long long* dbg;
   int solo_issue;
+  int split_k;                 // 1: grids that fill a fraction of the SMs are split along K (latency mode)
+  float* ws; size_t ws_bytes;  // split-K workspace
+  unsigned int* ws_cnt; size_t ws_cnt_n;
 };
+
+// Split-K factor for a grid of `tiles` work units on `cap` CTAs (or CTA pairs): the S in {1,2,3,4} dividing the K walk
+// that minimises waves / S, a part keeping at least `min_blocks` K blocks; S > 1 must win by more than its overhead
+// (a round trip of the accumulator through L2).
+static int choose_splitk(int tiles, int cap, int num_k, int ksub, int bk, int bn) {
+  // time model in units of one K block of one tile (BK/16 MMAs of ~BN/2 cycles, at least 128 cycles each for M = 128 in
+  // SS mode): waves * blocks per part + a split's overhead (accumulator out to L2, fence, S parts back in, ~4 us = 7,500
+  // cycles) expressed in the same unit
+  const double block_cycles = (bk / 16) * (bn >= 256 ? 128.0 : 128.0);
+  const double overhead = 7500.0 / block_cycles;
+  int best = 1;
+  double best_t = (double)ceil_div(tiles, cap) * num_k;
+  for (int S = 2; S <= 4; ++S) {
+    if (num_k % (S * ksub) != 0) continue;
+    const double t = (double)ceil_div(tiles * S, cap) * (num_k / S) + overhead;
+    if (t < 0.85 * best_t) { best_t = t; best = S; }
+  }
+  return best;
+}
 
 // Resolves a ConvCfg into the launch parameters of conv_tc_persist_kernel<BN,BK,PAIR> and launches it.
 template <int BN, int BK, bool PAIR>
 static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const LaunchEnv& env, const ConvCfg& cfg) {
+  constexpr bool CAN_SPLIT = BK == 64 && BN >= 64;     // the split-K instantiations that exist
   auto kern = conv_tc_persist_kernel<BN, BK, PAIR>;
   const int a_bytes = 128 * BK * 2, b_bytes = (PAIR ? BN / 2 : BN) * BK * 2;
   const int num_k = a.taps * a.kc_blocks;
@@ -649,6 +677,20 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
     ksub = std::min(ksub, num_k);
     while (ksub > 1 && avail / (ksub * sub_bytes) < 2) --ksub;
   }
+  // split-K (latency mode): direct epilogue only, N tiles of at least two chunks (the warps of a quarter then own fixed columns)
+  const int cap = PAIR ? env.num_sms / 2 : env.num_sms;
+  pa.splitk = 1;
+  if (CAN_SPLIT && env.split_k && env.ws && pa.n_tiles < 2 * cap) {
+    int S = choose_splitk(pa.n_tiles, cap, num_k, ksub, BK, BN);
+    const size_t unit_bytes = (size_t)(PAIR ? 2 : 1) * 128 * BN * 4;
+    while (S > 1 && ((size_t)pa.n_tiles * S * unit_bytes > env.ws_bytes || num_k % (S * ksub) != 0)) --S;
+    if ((size_t)pa.n_tiles * (PAIR ? 2 : 1) * CONV_TCP_EPI_WARPS > env.ws_cnt_n) S = 1;
+    if (S > 1 && pa.tma_epi) {       // the staging buffers return to the pipeline
+      pa.tma_epi = 0;
+    }
+    pa.splitk = S;
+    pa.ws = env.ws; pa.ws_cnt = env.ws_cnt;
+  }
   pa.ksub = ksub;
   const int stage_bytes = ksub * sub_bytes;
   pa.n_stages = std::min(CONV_TCP_MAX_STAGES, avail / stage_bytes);
@@ -659,7 +701,9 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
   op.launched_stages = pa.n_stages; op.launched_bstat = pa.b_stationary; op.launched_tma_epi = pa.tma_epi; op.launched_ksub = pa.ksub;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
-  lc.gridDim = PAIR ? dim3(2 * std::min(pa.n_tiles, env.num_sms / 2)) : dim3(std::min(pa.n_tiles, env.num_sms));
+  const int n_units = pa.n_tiles * pa.splitk;
+  op.launched_splitk = pa.splitk;
+  lc.gridDim = PAIR ? dim3(2 * std::min(n_units, env.num_sms / 2)) : dim3(std::min(n_units, env.num_sms));
   lc.blockDim = dim3(CONV_TCP_THREADS);
   lc.dynamicSmemBytes = smem;
   lc.stream = st;
@@ -676,6 +720,12 @@ static int launch_conv_tcp(cudaStream_t st, Op& op, const ConvArgs& a, const Lau
     ++na;
   }
   lc.attrs = attr; lc.numAttrs = na;
+  if constexpr (CAN_SPLIT) {
+    if (pa.splitk > 1) {
+      YB_CUDA(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<BN, BK, PAIR, true>, op.tmA, op.tmB[bn_index(PAIR ? BN / 2 : BN)], op.tmOut, op.tmRes, a, pa));
+      return YB_OK;
+    }
+  }
   YB_CUDA(cudaLaunchKernelEx(&lc, kern, op.tmA, op.tmB[bn_index(PAIR ? BN / 2 : BN)], op.tmOut, op.tmRes, a, pa));
   return YB_OK;
 }
@@ -790,10 +840,27 @@ static int launch_fused(yb_engine* e, Op& op, int n) {
 template <int BN, int BK, bool PAIR>
 static int set_tcp_attr() {
   YB_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<BN, BK, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
+  if constexpr (BK == 64 && BN >= 64)
+    YB_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<BN, BK, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_TCP_SMEM_MAX));
   return YB_OK;
 }
 // Per-device function attributes (opt-in shared-memory limits) and occupancy figures, set when an engine is created on
 // the device -- no process-global bookkeeping, so engines on several devices can be driven from several threads.
+// Split-K workspace: 2 * capacity work units of the widest pair tile (2 x 128 x 256 floats each), counters for every
+// (tile, pair rank, epilogue warp).
+static int set_split_k(yb_engine* e, bool on) {
+  if (on && !e->splitk_ws) {
+    const size_t units = 2 * (size_t)e->num_sms;
+    e->splitk_ws_bytes = units * 2 * 128 * 256 * 4;
+    e->splitk_cnt_n = units * 2 * CONV_TCP_EPI_WARPS;
+    YB_CUDA(cudaMalloc(&e->splitk_ws, e->splitk_ws_bytes));
+    YB_CUDA(cudaMalloc(&e->splitk_cnt, e->splitk_cnt_n * sizeof(unsigned int)));
+    YB_CUDA(cudaMemset(e->splitk_cnt, 0, e->splitk_cnt_n * sizeof(unsigned int)));
+  }
+  e->split_k = on ? 1 : 0;
+  return YB_OK;
+}
+
 static int set_kernel_attrs(yb_engine* e) {
   YB_TRY((set_tcp_attr<256, 64, true>())); YB_TRY((set_tcp_attr<128, 64, true>())); YB_TRY((set_tcp_attr<64, 64, true>()));
   YB_TRY((set_tcp_attr<128, 32, true>())); YB_TRY((set_tcp_attr<64, 32, true>()));
@@ -839,7 +906,8 @@ static int run_op(yb_engine* e, Op& op, int n, const ConvCfg* cfg_override = nul
     if (path == PATH_TC) {
       a.kc_blocks = op.cin / op.bk;
       a.im2col = !(op.ksize == 1 && op.stride == 1);
-      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate, e->dbg_counters, e->solo_issue};
+      const LaunchEnv env{e->device, e->num_sms, e->b_stationary, e->tma_epilogue, e->pdl, e->ablate, e->dbg_counters, e->solo_issue,
+                          e->split_k, e->splitk_ws, e->splitk_ws_bytes, e->splitk_cnt, e->splitk_cnt_n};
       ConvCfg cfg = cfg_override ? *cfg_override : op.cfg;
       if (cfg.pair && ceil_div(a.M, 128) < 2) cfg.pair = 0;          // a batch too small to form a pair of M tiles
       YB_TRY(dispatch_conv_tcp(st, op, a, env, cfg));
@@ -1508,6 +1576,8 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   if (fs) e->fuse_stem = atoi(fs);
   const char* fb = getenv("YB_FUSE_BLOCK");
   if (fb) e->fuse_block = atoi(fb);
+  const char* sk = getenv("YB_SPLIT_K");
+  if (sk && atoi(sk) != 0) e->split_k = -1;          // workspace allocated once the device is known (below)
   const char* fp = getenv("YB_FUSE_POOL");
   if (fp) e->fuse_pool = atoi(fp);
   const char* pp = getenv("YB_PIXEL_PAIRS");
@@ -1527,6 +1597,7 @@ int yb_engine_create(const yb_layer* plan, int n_layers, int in_h, int in_w, int
   if (r == YB_OK) {
     auto go = [&]() -> int {
       YB_TRY(set_kernel_attrs(e));
+      if (e->split_k < 0) YB_TRY(set_split_k(e, true));
       YB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
       YB_CUDA(cudaMalloc(&e->arena, e->arena_bytes));
       YB_CUDA(cudaMemset(e->arena, 0, e->arena_bytes));
@@ -1565,6 +1636,7 @@ void yb_engine_destroy(yb_engine* e) {
   for (Op& op : e->ops) { cudaFree(op.d_wt); cudaFree(op.d_wt32); cudaFree(op.d_scale); cudaFree(op.d_shift); }
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   cudaFree(e->dbg_counters);
+  cudaFree(e->splitk_ws); cudaFree(e->splitk_cnt);
   cudaFree(e->arena); cudaFree(e->input_dev[0]); cudaFree(e->input_dev[1]); cudaFree(e->d_u8_lut); cudaFree(e->scratch_f32);
   e->post.release();
   e->pre.release();
@@ -2001,7 +2073,10 @@ int yb_engine_autotune(yb_engine* e, int n, int reps) {
   if (!e->weights_loaded) return fail(YB_ERR_STATE, "yb_engine_autotune before yb_engine_load_weights");
   YB_TRY(set_device(e->device));
   clear_graphs(e);
+  const int split_was = e->split_k;
+  e->split_k = 0;                            // candidates are compared as plain kernels; split-K then applies on top
   const int rc = autotune(e, n, reps > 0 ? reps : 5);
+  e->split_k = split_was;
   clear_graphs(e);                           // the launch configurations changed
   return rc;
 }
@@ -2033,6 +2108,10 @@ int yb_engine_set_option(yb_engine* e, const char* name, int value) {
       cudaFree(e->dbg_counters);
       e->dbg_counters = nullptr;
     }
+  }
+  else if (!strcmp(name, "split_k")) {
+    YB_TRY(set_device(e->device));
+    YB_TRY(set_split_k(e, value != 0));
   }
   else if (!strcmp(name, "bstat")) e->b_stationary = value != 0;
   else if (!strcmp(name, "tma_epi")) e->tma_epilogue = value != 0;
@@ -2183,6 +2262,12 @@ int yb_engine_op_cfg(yb_engine* e, int op_index, int* bn, int* pair, int* bstat,
   if (tma_epi) *tma_epi = op.launched_tma_epi;
   if (stages) *stages = op.launched_stages;
   if (ksub) *ksub = op.launched_ksub;
+  return YB_OK;
+}
+
+int yb_engine_op_splitk(yb_engine* e, int op_index, int* splitk) {
+  if (!e || !splitk || op_index < 0 || op_index >= (int)e->ops.size()) return fail(YB_ERR_INVALID, "yb_engine_op_splitk: bad argument");
+  *splitk = e->ops[op_index].launched_splitk;
   return YB_OK;
 }
 

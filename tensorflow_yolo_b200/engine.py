@@ -210,7 +210,11 @@ class Engine(object):
     def op_cfg(self, op_index):
         v = [ctypes.c_int() for _ in range(6)]
         _lib.check(_lib.lib().yb_engine_op_cfg(self._h, op_index, *[ctypes.byref(x) for x in v]))
-        return dict(zip(("bn", "pair", "bstat", "tma_epi", "stages", "ksub"), [x.value for x in v]))
+        cfg = dict(zip(("bn", "pair", "bstat", "tma_epi", "stages", "ksub"), [x.value for x in v]))
+        sk = ctypes.c_int(1)
+        _lib.check(_lib.lib().yb_engine_op_splitk(self._h, op_index, ctypes.byref(sk)))
+        cfg["splitk"] = sk.value
+        return cfg
 
     def set_conv_impl(self, impl):
         _lib.check(_lib.lib().yb_engine_set_conv_impl(self._h, impl))

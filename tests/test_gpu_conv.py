@@ -284,3 +284,42 @@ def test_pixel_pair_view_is_bit_identical(monkeypatch):
         for a, b in zip(got[flag][:3], got["0"][:3]):
             assert np.array_equal(a, b)
     assert helpers.rel_err(got["1"][2], convstack.forward(topo, stream, x)) <= TOL
+
+
+def test_split_k_latency_mode_matches_the_plain_kernels():
+    """Option "split_k": convs whose grid fills a fraction of the SMs are computed by 2-4 work units per tile along K and
+    reduced in a fixed order.  Same products, a different fp32 summation order: the network output stays within bf16
+    rounding of the plain path and within TOL of the fp32 oracle, repeated runs are bit-identical (deterministic
+    reduction), some convs really run split, and switching the option off restores the plain bits."""
+    shape = (416, 416, 3)
+    net, topo, stream = helpers.build_v3(shape, 80, seed=2)
+    x = synth.images(2, shape[0], shape[1], seed=1)
+    eng = _engine(net, shape, 80, engine.YB_DECODE_V3, 2, stream)
+    eng.set_option("graph", 0)
+    eng.forward(x)
+    y_plain = eng.read_output()
+    eng.set_option("split_k", 1)
+    eng.forward(x)
+    y_split = eng.read_output()
+    factors = []
+    for i in range(len(eng.plan)):
+        try:
+            if eng.op_info(i)["path"] == 0:
+                factors.append(eng.op_cfg(i)["splitk"])
+        except Exception:
+            break                                                       # past the last launched op
+    assert max(factors) >= 2 and min(factors) >= 1, factors
+    eng.forward(x)
+    assert np.array_equal(eng.read_output(), y_split)                   # fixed summation order, whichever part arrives last
+    eng.set_option("graph", 1)                                          # and inside a captured graph
+    for _ in range(3):
+        eng.forward(x)
+        assert np.array_equal(eng.read_output(), y_split)
+    assert helpers.rel_err(y_split, y_plain) <= 1.5e-2, helpers.rel_err(y_split, y_plain)   # bf16 rounding flips through 75 layers
+    ref = convstack.forward(topo, stream, x)
+    assert helpers.rel_err(y_split, ref) <= TOL
+    eng.set_option("split_k", 0)
+    eng.set_option("graph", 0)
+    eng.forward(x)
+    assert np.array_equal(eng.read_output(), y_plain)
+    eng.close()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "latency.json"))
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--batches", default="1,2,4,8,16,32")
+    ap.add_argument("--split-k", type=int, default=-1, help="latency mode (option split_k): -1 = measure both, 0 / 1 = only that setting")
     args = ap.parse_args()
     import torch
     net, state, stream, shape = bench.build_network(416, "v3")
@@ -35,7 +36,11 @@ def main():
         g = torch.Generator(device="cuda"); g.manual_seed(1)
         x = torch.rand((n,) + shape, device="cuda", dtype=torch.float32, generator=g)
         row = {"batch": n}
-        for mode, name in ((0, "eager"), (1, "graph")):
+        variants = [(0, "eager", 0), (1, "graph", 0), (1, "graph_split_k", 1)]
+        if args.split_k >= 0:
+            variants = [(0, "eager", args.split_k), (1, "graph", args.split_k)]
+        for mode, name, sk in variants:
+            eng.set_option("split_k", sk)
             eng.set_option("graph", mode)
             for _ in range(5):
                 eng.forward(x); eng.detect_async(bench.THRESHOLD, bench.IOU_THRESHOLD)
@@ -52,6 +57,8 @@ def main():
             row[name] = {"device_ms_per_step": dev, "host_ms_per_step": wall, "images_per_s": n / (wall * 1e-3),
                          "graph_replays": eng.graph_replays() - r0}
         row["speedup_host"] = row["eager"]["host_ms_per_step"] / row["graph"]["host_ms_per_step"]
+        if "graph_split_k" in row:
+            row["split_k_factors"] = sorted(set(eng.op_cfg(i)["splitk"] for i in range(75)))
         out["rows"].append(row)
         print(json.dumps(row), flush=True)
         eng.close()

@@ -35,5 +35,5 @@ for op_i, (layer, ms) in enumerate(prof):
 tot = sum(r["us"] for r in rows)
 print("batch", B, "graph step ms", step_ms, "sum of per-op events us", tot)
 for r in sorted(rows, key=lambda r: -r["us"])[:28]:
-    print("op %3d L%3d %-16s k%d s%d path %d bn %3d pair %d st %2d ksub %d  %7.1f us  %6.0f TF/s" % (r["op"], r["layer"], r["out"], r["k"], r["s"], r["path"], r["cfg"]["bn"], r["cfg"]["pair"], r["cfg"]["stages"], r["cfg"]["ksub"], r["us"], r["gflop"] / max(r["us"], 1e-3) * 1e3 / 1e3))
-json.dump({"batch": B, "graph_step_ms": step_ms, "ops": rows}, open(os.path.join(ROOT, "gpurun_out", "small_batch_profile_b%d.json" % B), "w"), indent=0)
+    print("op %3d L%3d %-16s k%d s%d path %d bn %3d pair %d st %2d ksub %d splitk %d  %7.1f us  %6.0f TF/s" % (r["op"], r["layer"], r["out"], r["k"], r["s"], r["path"], r["cfg"]["bn"], r["cfg"]["pair"], r["cfg"]["stages"], r["cfg"]["ksub"], r["cfg"].get("splitk", 1), r["us"], r["gflop"] / max(r["us"], 1e-3)))
+json.dump({"batch": B, "graph_step_ms": step_ms, "ops": rows}, open(os.path.join(ROOT, "gpurun_out", "small_batch_profile_b%d%s.json" % (B, "_splitk" if os.environ.get("YB_SPLIT_K") else "")), "w"), indent=0)
