@@ -621,14 +621,16 @@ static int choose_splitk(int tiles, int cap, int num_k, int ksub, int bk, int bn
   // time model in units of one K block of one tile (BK/16 MMAs of ~BN/2 cycles, at least 128 cycles each for M = 128 in
   // SS mode): waves * blocks per part + a split's overhead (accumulator out to L2, fence, S parts back in, ~4 us = 7,500
   // cycles) expressed in the same unit
-  const double block_cycles = (bk / 16) * (bn >= 256 ? 128.0 : 128.0);
-  const double overhead = 7500.0 / block_cycles;
+  static const double overhead_cycles = getenv("YB_SPLIT_K_OVERHEAD") ? atof(getenv("YB_SPLIT_K_OVERHEAD")) : 7500.0;
+  static const double min_gain = getenv("YB_SPLIT_K_GAIN") ? atof(getenv("YB_SPLIT_K_GAIN")) : 0.85;
+  const double block_cycles = (bk / 16) * 128.0;
+  const double overhead = overhead_cycles / block_cycles;
   int best = 1;
   double best_t = (double)ceil_div(tiles, cap) * num_k;
   for (int S = 2; S <= 4; ++S) {
     if (num_k % (S * ksub) != 0) continue;
     const double t = (double)ceil_div(tiles * S, cap) * (num_k / S) + overhead;
-    if (t < 0.85 * best_t) { best_t = t; best = S; }
+    if (t < min_gain * best_t) { best_t = t; best = S; }
   }
   return best;
 }
@@ -1849,6 +1851,14 @@ static int forward_impl(yb_engine* e, const void* images, int dtype, int mem, in
     YB_CUDA(cudaMemcpyAsync(e->input_dev[slot], images, bytes, cudaMemcpyHostToDevice, e->copy_stream));
     YB_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
     YB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    e->cur_input = e->input_dev[slot];
+  } else if ((reinterpret_cast<uintptr_t>(images) & 15u) != 0) {
+    // a device pointer the TMA-fed first layers cannot address (conv_fused.cuh needs 16-byte alignment): one
+    // device-to-device copy into the staging buffer, on the compute stream
+    slot = e->stage_toggle;
+    e->stage_toggle ^= 1;
+    YB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_input_free[slot], 0));
+    YB_CUDA(cudaMemcpyAsync(e->input_dev[slot], images, bytes, cudaMemcpyDeviceToDevice, e->stream));
     e->cur_input = e->input_dev[slot];
   } else {
     e->cur_input = images;

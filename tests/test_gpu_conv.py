@@ -145,6 +145,20 @@ def test_arena_reuse_partial_batch_u8_and_device_input():
     assert np.array_equal(eng.read_output(), y)                       # u8 path == float path
     eng.forward(torch.from_numpy(xf).cuda())
     assert np.array_equal(eng.read_output(), y)
+    # a device tensor that does not start on a 16-byte boundary (a view into a larger buffer): the TMA-fed first layers
+    # cannot address it, the engine stages it -- same bits
+    big8 = torch.zeros(x8.size + 64, dtype=torch.uint8, device="cuda")
+    odd8 = big8[3:3 + x8.size].view(x8.shape)
+    odd8.copy_(torch.from_numpy(x8))
+    assert odd8.data_ptr() % 16 != 0
+    eng.forward(odd8)
+    assert np.array_equal(eng.read_output(), y)
+    bigf = torch.zeros(xf.size + 16, dtype=torch.float32, device="cuda")
+    oddf = bigf[1:1 + xf.size].view(xf.shape)
+    oddf.copy_(torch.from_numpy(xf))
+    assert oddf.data_ptr() % 16 != 0
+    eng.forward(oddf)
+    assert np.array_equal(eng.read_output(), y)
     with pytest.raises(Exception):
         eng.forward(np.zeros((9, 128, 160, 3), np.float32))           # > max_batch
     with pytest.raises(Exception):

@@ -43,7 +43,8 @@ def main():
             ph, pw, pc = p["out_hwc"]
             e["flop"] += 2.0 * B * ph * pw * pc * p["ksize"] * p["ksize"] * p["cin"]
             e["bytes"] += B * (ph * pw * p["cin"] * (2 if p["cin"] > 3 else 4)) - B * (h * s * w * s * cin * 2)
-            e["cfg"] = "fused pair: {}x{} {}->{} + this (mma.sync producer, tcgen05 BN64 BK32)".format(p["ksize"], p["ksize"], p["cin"], pc)
+            e["cfg"] = "fused pair: {}x{} {}->{} ({}) + this (tcgen05 BN64 BK32)".format(
+                p["ksize"], p["ksize"], p["cin"], pc, "mma.sync producer" if p["cin"] == 3 else "tcgen05 producer, the TMA patch as operand")
         else:
             e["cfg"] = "BN{} BK{}{}".format(o["bn"], o["bk"], " pair" if o.get("pair") else "") if o["path"] == 0 else "mma.sync"
     tot_ms = sum(e["ms"] for e in g.values())
