@@ -4,7 +4,7 @@
 // they compute on: conv 3->32 @416^2 writes 1.4 GB per 128 images only for the stride-2 conv behind it to read them
 // back nine times through im2col TMA loads.  Here ONE kernel computes both layers of such a pair:
 //
-//   input patch by TMA (tile mode, zero-filled outside the image)  ->  producer conv (small K, on mma.sync)  ->  bf16
+//   input patch by TMA (tile mode, zero-filled outside the image)  ->  producer conv (small K)  ->  bf16
 //   activations written straight into K-major, 64-byte-swizzled operand tiles of the 3x3 consumer conv in shared
 //   memory  ->  tcgen05.mma (M=128, N=64, K=9*32), accumulator in TMEM  ->  BN / leaky (/ residual) epilogue  ->  TMA store.
 //
@@ -22,26 +22,27 @@
 // start address is a multiple of 1024 bytes.  A producer pixel is stored 3 times (stride 1) or at most twice (stride 2).
 //
 // Arithmetic is that of the unfused kernels: the STEM producer runs the mma.sync sequence of conv_first_mma_kernel
-// (same K order, bit-identical results), the BLOCK producer sums its K=64 in four mma.sync steps (fp32 summation order
-// differs from the tcgen05 1x1 conv), the consumer's K walk (tap-major, two K=16 MMAs per tap) is
-// conv_tc_persist_kernel<64,32>'s.  BN and the leaky multiply run on packed fp32 pairs (fma.rn.f32x2 / mul.rn.f32x2:
-// the same IEEE operations, two per instruction).
+// (same K order, bit-identical results), the BLOCK producer is a tcgen05 1x1 conv like the stand-alone one (K = 64 in four
+// K = 16 steps), the consumer's K walk (tap-major, two K=16 MMAs per tap) is conv_tc_persist_kernel<64,32>'s.  BN and the
+// leaky multiply run on packed fp32 pairs (fma.rn.f32x2 / mul.rn.f32x2: the same IEEE operations, two per instruction).
 //
-// The kernels are instruction-issue bound (ncu: ~2 warp instructions per cycle per SM before this layout), so everything
-// per tile is organised to cost few instructions: no integer division in the tile walk, every shared-memory address of
-// the producer loops is one per-thread register plus a compile-time offset, bf16 pairs of the first conv's im2col rows
-// are fetched with one aligned 32-bit load from one of two patch copies (the second shifted by one element), input
-// patches arrive by TMA.
+// What bounds them: the first version was instruction-issue bound (~2 warp instructions per cycle per
+// SM, half of them address arithmetic), so everything per tile costs few instructions: no integer division in the tile
+// walk, every shared-memory address of the producer loops is one per-thread register plus a compile-time offset, bf16
+// pairs of the first conv's im2col rows are fetched with one aligned 32-bit load from one of two patch copies (the
+// second shifted by one element), input patches arrive by TMA (requested into L2 eight tiles ahead).  Then: warp-level
+// mma.sync shares the tensor pipe with tcgen05.mma and stalls its warps while the consumer's MMAs run, and issuing 18
+// MMAs blocks the issuing thread for most of their execution -- hence a warp of its own for MMA issue, and the BLOCK
+// producer on tcgen05.  What is left is shared-memory bandwidth (operand reads of the MMAs + operand stores + staging).
 //
-// Warp roles (one persistent CTA per SM, 544 threads):
-//   warps 0-11  producers: (STEM) convert the raw uint8 / float patch to the two bf16 copies; producer conv on three
-//               (STEM) or one (BLOCK) mma tiles of 16 pixels each, operand stores into A[tile&1]; named barrier 1 among
-//               themselves, mbarrier a_full[] towards the MMA issuer
-//   warps 12-15 epilogue, TMEM lane quarter = warp & 3, both 32-column chunks: waits mma_done, BN/leaky(/residual, read
-//               from the input patch still in shared memory), swizzled staging, 4-D TMA store; arrives on acc_empty[].
+// STEM warp roles (one persistent CTA per SM, 544 threads; BLOCK: see block_fused_kernel):
+//   warps 0-11  producers: convert the raw uint8 / float patch to the two bf16 copies; producer conv on three mma tiles
+//               of 16 pixels each, operand stores into A[tile&1]; named barrier 1 among themselves, mbarrier a_full[]
+//               towards the MMA issuer
+//   warps 12-15 epilogue, TMEM lane quarter = warp & 3, both 32-column chunks: waits mma_done, BN/leaky, swizzled
+//               staging, 4-D TMA store; arrives on acc_empty[]
 //   warp 16     owns TMEM; one elected lane requests the input patches (L2 prefetch 8 tiles ahead, TMA load 2 tiles ahead)
-//               and issues the MMAs of every tile (waits a_full / acc_empty, 18 MMAs, commit -> mma_done[]).  A warp of
-//               its own because the issue of 18 MMAs blocks for most of their execution time (the queue is short).
+//               and issues the MMAs of every tile (waits a_full / acc_empty, 18 MMAs, commit -> mma_done[])
 // mma_done[b] doubles as "A[b] may be overwritten" for the producers.
 #pragma once
 #include "aux_kernels.cuh"
@@ -53,7 +54,7 @@ constexpr int FUSE_PRODUCER_WARPS = 12;
 constexpr int FUSE_PRODUCER_THREADS = FUSE_PRODUCER_WARPS * 32;
 constexpr int FUSE_EPI_WARP0 = 12, FUSE_EPI_WARPS = 4;
 constexpr int FUSE_MMA_WARP = 16;                         // owns TMEM; one elected lane requests input patches and issues the MMAs
-constexpr int FUSE_THREADS = (FUSE_MMA_WARP + 1) * 32;    // 544 (17 warps: 120 registers per thread)
+constexpr int FUSE_THREADS = (FUSE_MMA_WARP + 1) * 32;    // 544 (17 warps, register file allocated as for 20: 96 per thread)
 constexpr int FUSE_TH = 8, FUSE_TW = 16;                  // output tile of the consumer conv
 constexpr int FUSE_CMID = 32, FUSE_COUT = 64;
 constexpr int FUSE_ROW_BYTES = FUSE_TW * FUSE_CMID * 2;   // one operand row of 16 pixels: 1024 bytes
