@@ -131,7 +131,9 @@ int yb_engine_load_weights(yb_engine* e, const float* stream, size_t n, size_t* 
 /* Replaces sess.run(net[-1].out, {net[0].out: x_batch}) (net/yolo.py:83).  images: NHWC,
  * n*in_h*in_w*in_c elements of dtype (float32 in [0,1], or uint8 which is scaled by 1/255),
  * in host or device memory.  Asynchronous with respect to the host on the engine's stream;
- * results stay on the device. */
+ * results stay on the device.  A device pointer should be 16-byte aligned (the first layers read the
+ * images through a TMA tensor map); one that is not is first copied, device to device, into the
+ * engine's staging buffer -- same results. */
 int yb_engine_forward(yb_engine* e, const void* images, int dtype, int mem, int n);
 
 /* Replaces base.generate_test_batch / preprocess_image (net/base.py:115-168) + the forward: takes the decoded 8-bit
