@@ -149,6 +149,16 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0,
                "r"(c2)
                : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -949,6 +959,246 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   if (warp == BLK_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<BLK_TMEM_COLS>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// CONVPOOL: conv 3x3 s1 32->64 + BN + leaky + 2x2/2 max pool (Darknet-19's second conv, net/v2.py:23-24,
+// net/layers.py:70-81) -- the consumer of the fused block without a producer conv, the pool taken in registers
+// ================================================================================================
+// The 10 x 18 x 32-channel input patch arrives as one TMA box (SWIZZLE_64B, zero outside the image = the conv's padding);
+// six warps copy it into the three kw copies of the operand (no arithmetic), the 18 MMAs are those of the block kernel.
+// Epilogue: a warp holds tile rows 2q (lanes 0-15) and 2q+1 (lanes 16-31), one pixel per lane, so the 2x2 window of pooled
+// pixel (q, c/2) is lanes {c, c^1} x {row, row^16}: two shuffles and two packed bf16 maxima per register.  max commutes with
+// the monotone bf16 rounding: bit-identical to conv -> bf16 -> maxpool2_kernel.  Only the pooled 4 x 8 x 64 tile is written
+// (one TMA store of 8 pixels x 16 channels per warp); the full-resolution activation never exists.  The epilogue is the
+// long pole -- per warp a chain of dependent shuffles -- and it is latency-, not throughput-bound (ncu: its warps were busy
+// 96% of the time at one instruction per 9 cycles with 4 or 8 warps), hence sixteen warps of 16 channels each with their
+// scale / shift in registers.
+constexpr int CP_PROD_WARPS = 6;
+constexpr int CP_MMA_WARP = 6;                                           // (warp 7 idles: the epilogue warps must start at a multiple of 4)
+constexpr int CP_EPI_WARP0 = 8, CP_EPI_WARPS = 16;                       // four epilogue warps per TMEM lane quarter: 16 columns each
+constexpr int CP_EPI_COLS = FUSE_COUT / (CP_EPI_WARPS / 4);              // 16
+constexpr int CP_THREADS = (CP_EPI_WARP0 + CP_EPI_WARPS) * 32;           // 768
+constexpr int CP_PATCH_TX = BLOCK_PATCH_PIX * 64;                        // 11,520
+constexpr int CP_PATCH_STAGE = 12288;
+constexpr int CP_IN_STAGES = 4;
+constexpr int CP_EPI_BYTES = CP_EPI_WARPS * 2 * 256;                     // per epilogue warp two buffers of 8 pooled pixels x 32 B
+constexpr int CP_BUFS = 4;                                               // operand buffers = TMEM accumulators (64 columns each)
+constexpr int FUSE_SMEM_CONVPOOL = 1024 + FUSE_HEADER + FUSE_B_BYTES + CP_BUFS * BLOCK_A_BYTES + CP_IN_STAGES * CP_PATCH_STAGE + CP_EPI_BYTES;
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+convpool_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const FuseArgs a) {
+  extern __shared__ __align__(1024) uint8_t fuse_smem_raw[];
+  uint8_t* smem = fuse_smem_raw + ((1024u - (smem_u32(fuse_smem_raw) & 1023u)) & 1023u);
+  FuseSmem s;
+  s.a_full = reinterpret_cast<uint64_t*>(smem);              // [4] [4] [4] [1] [4] [4]: 21 barriers, bytes [0, 168)
+  s.mma_done = s.a_full + CP_BUFS;
+  s.acc_empty = s.mma_done + CP_BUFS;
+  s.b_full = s.acc_empty + CP_BUFS;
+  s.in_full = s.b_full + 1;
+  s.in_empty = s.in_full + FUSE_MAX_IN_STAGES;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(smem + 256);
+  s.bs = smem + FUSE_HEADER;
+  s.a0 = s.bs + FUSE_B_BYTES;
+  s.in = s.a0 + CP_BUFS * BLOCK_A_BYTES;
+  s.epi = s.in + CP_IN_STAGES * CP_PATCH_STAGE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < CP_BUFS; ++i) {
+      mbar_init(&s.a_full[i], CP_PROD_WARPS);
+      mbar_init(&s.mma_done[i], 1);
+      mbar_init(&s.acc_empty[i], CP_EPI_WARPS);
+    }
+    mbar_init(s.b_full, 1);
+    for (int i = 0; i < CP_IN_STAGES; ++i) {
+      mbar_init(&s.in_full[i], 1);
+      mbar_init(&s.in_empty[i], CP_PROD_WARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == CP_MMA_WARP) {
+    tmem_alloc<CP_BUFS * FUSE_COUT>(s.tmem_ptr);
+    if (elect_one()) {
+      mbar_expect_tx(s.b_full, (uint32_t)FUSE_B_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmB, s.b_full, s.bs + tap * FUSE_BTAP_BYTES, tap * FUSE_CMID, 0);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+  const uint32_t patch_u32 = smem_u32(s.in);
+
+  if (warp < CP_PROD_WARPS) {
+    // ---- copy producers: this thread owns patch pixel f of every tile ----
+    const int q = warp & 3, mt = warp >> 2;
+    const int f = 128 * mt + 32 * q + lane;
+    const bool valid = f < BLOCK_PATCH_PIX;
+    const int py = f / BLOCK_PATCH_W, px = f - py * BLOCK_PATCH_W;
+    const uint32_t src_ofs = (uint32_t)(valid ? f : 0) * 64u, src_sw = (uint32_t)(f >> 1) & 3u;
+    uint32_t dofs[3], dsw[3];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int c = px - kw;
+      const bool v = valid && c >= 0 && c < FUSE_TW;
+      const int row = py * FUSE_TW + c;
+      dofs[kw] = v ? (uint32_t)(kw * BLOCK_COPY_BYTES + row * 64) : 0xFFFFFFFFu;
+      dsw[kw] = (uint32_t)((row >> 1) & 3);
+    }
+    int it = 0, in_stage = 0;
+    uint32_t in_phase = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & (CP_BUFS - 1);
+      const uint32_t patch = patch_u32 + (uint32_t)(in_stage * CP_PATCH_STAGE) + src_ofs;
+      mbar_wait(&s.in_full[in_stage], in_phase);
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = lds128(patch + (((uint32_t)j ^ src_sw) << 4));
+      if (it >= CP_BUFS) mbar_wait(&s.mma_done[buf], (uint32_t)((it / CP_BUFS) - 1) & 1u);       // the MMAs of tile it-4 have read A[buf]
+      const uint32_t a_base = smem_u32(s.a0) + (uint32_t)(buf * BLOCK_A_BYTES);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+        if (dofs[kw] != 0xFFFFFFFFu) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sts128(a_base + dofs[kw] + (((uint32_t)j ^ dsw[kw]) << 4), v[j].x, v[j].y, v[j].z, v[j].w);
+        }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s.in_empty[in_stage]);          // the patch values are in the operand (the stores above consumed the loads)
+        mbar_arrive(&s.a_full[buf]);
+      }
+      if (++in_stage == CP_IN_STAGES) { in_stage = 0; in_phase ^= 1u; }
+    }
+  } else if (warp >= CP_EPI_WARP0) {
+    // ---- pooled epilogue ----
+    const int quarter = warp & 3, ew = warp - CP_EPI_WARP0, part = ew >> 2;       // columns [16 * part, 16 * part + 16)
+    const bool leaky2 = a.leaky2 != 0;
+    const bool writer = (lane & 17) == 0;             // even column of the even row: lanes 0, 2, ..., 14
+    uint64_t sc[CP_EPI_COLS / 2], sh[CP_EPI_COLS / 2];
+#pragma unroll
+    for (int j = 0; j < CP_EPI_COLS / 2; ++j) {
+      sc[j] = f2_pack(a.scale2[part * CP_EPI_COLS + 2 * j], a.scale2[part * CP_EPI_COLS + 2 * j + 1]);
+      sh[j] = f2_pack(a.shift2[part * CP_EPI_COLS + 2 * j], a.shift2[part * CP_EPI_COLS + 2 * j + 1]);
+    }
+    TileWalk tw;
+    tw.init(a.tiles_w, a.tiles_h, blockIdx.x, gridDim.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & (CP_BUFS - 1);
+      uint8_t* buf = s.epi + (ew * 2 + (it & 1)) * 256;
+      // staging: 8 pooled pixels x 32 bytes (16 channels), no swizzle (two 16-byte chunks per row)
+      const uint32_t row = smem_u32(buf) + (uint32_t)(lane >> 1) * 32u;
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      mbar_wait(&s.mma_done[acc], (uint32_t)(it / CP_BUFS) & 1u);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * FUSE_COUT + part * CP_EPI_COLS), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc_empty[acc]);  // the accumulator is in registers: hand it back
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y0, y1;
+        bn_leaky2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), sc[j], sh[j], leaky2, y0, y1);
+        pk[j] = pack_bf16(y0, y1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+        const __nv_bfloat162 mm = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]), *reinterpret_cast<const __nv_bfloat162*>(&o));
+        pk[j] = *reinterpret_cast<const uint32_t*>(&mm);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, pk[j], 16);
+        const __nv_bfloat162 mm = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]), *reinterpret_cast<const __nv_bfloat162*>(&o));
+        pk[j] = *reinterpret_cast<const uint32_t*>(&mm);
+      }
+      if (writer) {
+        sts128(row, pk[0], pk[1], pk[2], pk[3]);
+        sts128(row + 16u, pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&tmOut, buf, part * CP_EPI_COLS, tw.q0() >> 1, (tw.p0() >> 1) + quarter, tw.img);
+        tma_store_commit();
+      }
+      tw.advance();
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp == CP_MMA_WARP) {
+    if (elect_one()) {
+      TileWalk pf, l2;
+      pf.init(a.tiles_w, a.tiles_h, blockIdx.x, gridDim.x);
+      l2 = pf;
+      int pf_tile = blockIdx.x, pf_stage = 0, l2_tile = blockIdx.x;
+      uint32_t pf_phase = 0;
+      bool pf_wrapped = false;
+      auto prefetch_one = [&]() {
+        if (pf_tile < a.n_tiles) {
+          if (pf_wrapped) mbar_wait(&s.in_empty[pf_stage], pf_phase);
+          mbar_expect_tx(&s.in_full[pf_stage], (uint32_t)CP_PATCH_TX);
+          tma_load_4d(&tmIn, &s.in_full[pf_stage], patch_u32 + (uint32_t)(pf_stage * CP_PATCH_STAGE), 0, pf.q0() - 1, pf.p0() - 1, pf.img);
+          pf.advance();
+          pf_tile += gridDim.x;
+          if (++pf_stage == CP_IN_STAGES) { pf_stage = 0; if (pf_wrapped) pf_phase ^= 1u; pf_wrapped = true; }
+        }
+      };
+      auto l2_one = [&]() {
+        if (l2_tile < a.n_tiles) {
+          tma_prefetch_l2_4d(&tmIn, 0, l2.q0() - 1, l2.p0() - 1, l2.img);
+          l2.advance();
+          l2_tile += gridDim.x;
+        }
+      };
+      for (int i = 0; i < FUSE_L2_AHEAD; ++i) l2_one();
+      for (int i = 0; i < CP_IN_STAGES - 1; ++i) prefetch_one();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        l2_one();
+        prefetch_one();
+        {   // 18 MMAs of tile `it` into accumulator / from operand buffer it % 4
+          constexpr uint32_t idesc = make_idesc<FUSE_COUT>();
+          const int buf = it & (CP_BUFS - 1);
+          const uint32_t use = (uint32_t)(it / CP_BUFS);
+          if (it == 0) mbar_wait(s.b_full, 0);
+          if (it >= CP_BUFS) mbar_wait(&s.acc_empty[buf], (use - 1u) & 1u);
+          mbar_wait(&s.a_full[buf], use & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.a0) + (uint32_t)(buf * BLOCK_A_BYTES);
+          const uint32_t b_addr = smem_u32(s.bs);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * FUSE_COUT);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint64_t da = make_kmajor_desc<FUSE_CMID>(a_addr + (uint32_t)(kw * BLOCK_COPY_BYTES + kh * FUSE_ROW_BYTES));
+            const uint64_t db = make_kmajor_desc<FUSE_CMID>(b_addr + (uint32_t)(tap * FUSE_BTAP_BYTES));
+#pragma unroll
+            for (int k = 0; k < FUSE_CMID / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&s.mma_done[buf]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == CP_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<CP_BUFS * FUSE_COUT>(tmem_base);
   }
 }
 

@@ -305,7 +305,7 @@ struct Buf {
 };
 enum OpKind { OP_CONV = 0, OP_MAXPOOL, OP_ADD, OP_UPSAMPLE, OP_REORG, OP_COPY };
 enum ConvPath { PATH_TC = 0, PATH_DIRECT = 1, PATH_SIMT = 2, PATH_FUSED = 3 };
-enum FuseKind { FUSE_NONE = 0, FUSE_STEM = 1, FUSE_BLOCK = 2 };
+enum FuseKind { FUSE_NONE = 0, FUSE_STEM = 1, FUSE_BLOCK = 2, FUSE_CONVPOOL = 3 };
 
 // How one tcgen05 conv is launched.  compile_plan fills in a heuristic; yb_engine_autotune replaces it with the
 // fastest measured candidate.
@@ -336,7 +336,7 @@ struct Op {
   int px_pair = 0;
   int kw = 0, stride_w = 0, pad_w = 0;      // kernel width, stride and low padding along W (= ksize, stride, pad unless px_pair == 2)
   // Two-layer fusion (conv_fused.cuh): this op is the 3x3 consumer conv and also computes its producer conv
-  // ops[fuse_src] (which is then never launched: skip) -- FUSE_STEM: first conv 3->32 + 3x3 s2 32->64;
+  // ops[fuse_src] (which is then never launched: skip; FUSE_CONVPOOL has no producer: fuse_src = -1) -- FUSE_STEM: first conv 3->32 + 3x3 s2 32->64;
   // FUSE_BLOCK: 1x1 64->32 + 3x3 s1 32->64 + shortcut.
   int fuse_kind = FUSE_NONE, fuse_src = -1;
   bool skip = false;
@@ -808,7 +808,7 @@ static int stem_input_map(yb_engine* e, const void* ptr, int dtype, const CUtens
 
 // conv_fused.cuh: one persistent CTA per SM over 8 x 16 output tiles
 static int launch_fused(yb_engine* e, Op& op, int n) {
-  const Op& pp = e->ops[op.fuse_src];
+  const Op& pp = e->ops[op.fuse_kind == FUSE_CONVPOOL ? 0 : op.fuse_src];      // (unused for conv + pool)
   FuseArgs a;
   memset(&a, 0, sizeof(a));
   a.n_img = n; a.Ho = op.Ho; a.Wo = op.Wo; a.H = pp.in.h; a.W = pp.in.w;
@@ -821,7 +821,10 @@ static int launch_fused(yb_engine* e, Op& op, int n) {
   a.dbg = e->dbg_counters;
   const int grid = std::min(a.n_tiles, e->num_sms);
   const CUtensorMap& tmB = op.tmB[bn_index(FUSE_COUT)];
-  if (op.fuse_kind == FUSE_STEM) {
+  if (op.fuse_kind == FUSE_CONVPOOL) {
+    a.H = op.Ho; a.W = op.Wo;
+    convpool_fused_kernel<<<grid, CP_THREADS, FUSE_SMEM_CONVPOOL, e->stream>>>(op.tmIn4, tmB, op.tmOut4, a);
+  } else if (op.fuse_kind == FUSE_STEM) {
     a.w1 = pp.d_wt32;
     const CUtensorMap* tmIn = nullptr;
     YB_TRY(stem_input_map(e, e->cur_input, e->cur_input_dtype, &tmIn));
@@ -872,6 +875,7 @@ static int set_kernel_attrs(yb_engine* e) {
   YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_smem_stem<true>()));
   YB_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fuse_smem_stem<false>()));
   YB_CUDA(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_BLOCK));
+  YB_CUDA(cudaFuncSetAttribute(convpool_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSE_SMEM_CONVPOOL));
   const int smem_first = (FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2, smem_pool = (2 * FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2;
   if (smem_first <= 200 * 1024) {
     YB_CUDA(cudaFuncSetAttribute(conv_first_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1067,6 +1071,12 @@ static int compile_plan(yb_engine* e) {
              P[i].filters % 32 == 0 && P[i].batch_norm && e->shape[i].h % 2 == 0 && e->shape[i].w % 2 == 0 && (e->W * 3) % 4 == 0 &&
              (2 * FIRST_ROWS + 2) * FIRST_ROW_ELEMS(e->W) * 2 <= 200 * 1024 &&
              (e->fuse_pool == 2 || (e->fuse_pool == 1 && !e->keep_all))) { absorbed_into[i] = j; out_mode[i] = OUT_POOL2; }
+    // Darknet-19's second conv + max pool (net/v2.py:23-24): conv 3x3 32 -> 64 on the tcgen05 consumer of conv_fused.cuh,
+    // pooled in the epilogue's registers (convpool_fused_kernel).  The input must be a plain activation of its own.
+    else if (P[j].kind == YB_MAXPOOL && P[j].stride == 2 && P[j].ksize == 2 && (P[P[i].src[0]].kind == YB_MAXPOOL || P[P[i].src[0]].kind == YB_CONV) &&
+             P[i].ksize == 3 && P[i].stride == 1 && P[i].filters == FUSE_COUT && P[i].batch_norm && e->shape[P[i].src[0]].c == FUSE_CMID &&
+             e->shape[i].h % FUSE_TH == 0 && e->shape[i].w % FUSE_TW == 0 &&
+             (e->fuse_pool == 2 || (e->fuse_pool == 1 && !e->keep_all))) { absorbed_into[i] = j; out_mode[i] = OUT_POOL2; }
   }
   std::vector<bool> absorbs(n, false);
   for (int i = 0; i < n; ++i) if (absorbed_into[i] >= 0) absorbs[absorbed_into[i]] = true;
@@ -1164,6 +1174,12 @@ static int compile_plan(yb_engine* e) {
           e->view[pp.layer].buf = -1;
           op.in = pp.in;
         }
+      }
+      if (op.out_mode == OUT_POOL2 && op.in.buf != -2) {        // conv 32 -> 64 + max pool: convpool_fused_kernel
+        if (!(tma_ok && op.cin == FUSE_CMID && op.cout == FUSE_COUT && op.in.buf >= 0 && op.in.ld == FUSE_CMID && op.in.coff == 0 &&
+              !op.out.f32 && !op.has_res))
+          return fail(YB_ERR_INVALID, "layer %d: conv + max pool fusion needs a plain 32-channel bf16 input (pitch %d, offset %d)", i, op.in.ld, op.in.coff);
+        op.fuse_kind = FUSE_CONVPOOL;
       }
       if (op.fuse_kind) {
         op.path = PATH_FUSED;
@@ -1295,13 +1311,33 @@ static int build_tensor_maps(yb_engine* e) {
       const int K = 9 * FUSE_CMID;
       memset(op.tmB, 0, sizeof(op.tmB));
       YB_TRY(make_tiled_map(&op.tmB[bn_index(FUSE_COUT)], op.d_wt, op.cout_pad, K, K, FUSE_COUT, FUSE_CMID));
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r;
+      if (op.fuse_kind == FUSE_CONVPOOL) {
+        // pooled output (C, Wo/2, Ho/2, N), one box of 8 pixels x 64 channels per epilogue warp; input (C = 32, W, H, N), one
+        // 10 x 18 patch per tile, 64-byte rows
+        cuuint64_t odims[4] = {(cuuint64_t)op.cout, (cuuint64_t)(op.Wo / 2), (cuuint64_t)(op.Ho / 2), (cuuint64_t)e->max_batch};
+        cuuint64_t ostr[3] = {(cuuint64_t)op.out.ld * 2, (cuuint64_t)(op.Wo / 2) * op.out.ld * 2, (cuuint64_t)(op.Ho / 2) * (op.Wo / 2) * op.out.ld * 2};
+        cuuint32_t obox[4] = {(cuuint32_t)CP_EPI_COLS, 8, 1, 1};          // per epilogue warp: 8 pooled pixels x 16 channels
+        r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), odims, ostr, obox, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(pooled output) failed (%d) for layer %d", (int)r, op.layer);
+        cuuint64_t idims[4] = {(cuuint64_t)FUSE_CMID, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
+        cuuint64_t istr[3] = {(cuuint64_t)op.in.ld * 2, (cuuint64_t)op.Wo * op.in.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.in.ld * 2};
+        cuuint32_t ibox[4] = {(cuuint32_t)FUSE_CMID, (cuuint32_t)BLOCK_PATCH_W, (cuuint32_t)BLOCK_PATCH_H, 1};
+        r = g_encode_tiled(&op.tmIn4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.in), idims, istr, ibox, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(conv + pool input) failed (%d) for layer %d", (int)r, op.layer);
+        continue;
+      }
       cuuint64_t dims[4] = {(cuuint64_t)op.cout, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
       cuuint64_t strides[3] = {(cuuint64_t)op.out.ld * 2, (cuuint64_t)op.Wo * op.out.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.out.ld * 2};
       cuuint32_t box[4] = {(cuuint32_t)FUSE_COUT, (cuuint32_t)FUSE_TW, 2, 1};      // 128-byte rows: SWIZZLE_128B
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      CUresult r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), dims, strides, box, es,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D output) failed (%d) for layer %d", (int)r, op.layer);
       memset(&op.tmIn4, 0, sizeof(op.tmIn4));
       if (op.fuse_kind == FUSE_BLOCK) {       // the producer's input patch (its centre is the residual): 10 x 18 pixels x 64 channels
@@ -2258,7 +2294,7 @@ int yb_engine_op_info(yb_engine* e, int op_index, int* layer, int* path, int* bn
   auto conv_flops = [](const Op& o) { return 2.0 * o.Ho * o.Wo * o.cout * o.ksize * o.ksize * o.cin / (o.px_pair ? 2.0 : 1.0); };
   if (flops_per_image) {
     *flops_per_image = (op.kind == OP_CONV && !op.skip) ? conv_flops(op) : 0.0;
-    if (op.kind == OP_CONV && op.fuse_kind) *flops_per_image += conv_flops(e->ops[op.fuse_src]);     // both layers of a fused pair
+    if (op.kind == OP_CONV && op.fuse_kind && op.fuse_src >= 0) *flops_per_image += conv_flops(e->ops[op.fuse_src]);     // both layers of a fused pair
   }
   return YB_OK;
 }

@@ -73,8 +73,10 @@ def test_fused_is_batch_position_invariant(monkeypatch):
 
 
 @pytest.mark.parametrize("shape,n,u8", [((96, 64, 3), 3, False), ((416, 416, 3), 2, True)])
-def test_first_conv_with_max_pool_in_registers_is_bit_identical(monkeypatch, shape, n, u8):
-    """Darknet-19's conv 3->32 + 2x2 max pool (net/v2.py:20-22) in one kernel: the pooled map equals conv -> maxpool2."""
+def test_convs_with_max_pool_in_registers_are_bit_identical(monkeypatch, shape, n, u8):
+    """Darknet-19's conv 3->32 + 2x2 max pool and conv 32->64 + 2x2 max pool (net/v2.py:20-24), each in one kernel: the
+    pooled maps equal conv -> bf16 -> maxpool2 bit for bit (max commutes with the monotone bf16 rounding; the second conv
+    walks K like the stand-alone tcgen05 kernel)."""
     net, topo, stream = helpers.build_v2(shape, 20, seed=3)
     if u8:
         x = np.random.RandomState(6).randint(0, 256, (n,) + shape).astype(np.uint8)
@@ -89,13 +91,16 @@ def test_first_conv_with_max_pool_in_registers_is_bit_identical(monkeypatch, sha
         eng = engine.Engine(net[0]._yb_state.plan(), shape, 20, engine.YB_DECODE_V2, max_batch=n)
         eng.load_weights(stream)
         eng.forward(x)
-        out[fuse] = (eng.read_layer(2), eng.read_output(), eng.launch_count()[0])
+        out[fuse] = (eng.read_layer(2), eng.read_layer(4), eng.read_output(), eng.launch_count()[0])
         if fuse == "2":
-            with pytest.raises(Exception, match="fused"):
-                eng.read_layer(1)
+            for conv in (1, 3):
+                with pytest.raises(Exception, match="fused"):
+                    eng.read_layer(conv)
         eng.close()
-    assert out["2"][2] == out["0"][2] - 1                          # one launch fewer
-    assert np.array_equal(out["2"][0], out["0"][0])                # pooled activation, bit for bit
-    assert np.array_equal(out["2"][1], out["0"][1])                # and therefore the whole network output
+    assert out["2"][3] == out["0"][3] - 2                          # two launches fewer
+    assert np.array_equal(out["2"][0], out["0"][0])                # first pooled activation, bit for bit
+    assert np.array_equal(out["2"][1], out["0"][1])                # second pooled activation
+    assert np.array_equal(out["2"][2], out["0"][2])                # and therefore the whole network output
     _, outs = convstack.forward(topo, stream, xf, return_all=True)
     assert helpers.rel_err(out["2"][0], outs[2].permute(0, 2, 3, 1).numpy()) <= TOL
+    assert helpers.rel_err(out["2"][1], outs[4].permute(0, 2, 3, 1).numpy()) <= TOL

@@ -13,11 +13,11 @@ using namespace yb;
 
 template <int M, int N>
 __global__ void __launch_bounds__(128, 1) probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
-                                                       float* __restrict__ D, int iters, long long* cycles) {
+                                                       float* __restrict__ D, int iters, long long* cycles, int distinct) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // M x 64 B
-  uint8_t* sB = smem + 128 * 64;                        // N x 64 B
+  uint8_t* sB = smem + 4 * 128 * 64;                    // N x 64 B (x 4 tiles in the distinct-operand timing mode)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_ptr;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -41,6 +41,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __nv_bfloat16* __re
     const uint64_t db = make_kmajor_desc<32>(smem_u32(sB));
     constexpr uint32_t idesc = make_idesc_m<N, M>();
     const long long t0 = clock64();
+    if (distinct) {
+      // successive MMAs read different operand tiles: A tile t at +t*M*64 bytes, B tile t at +t*N*64 bytes (garbage data: timing only)
+      for (int it = 0; it < iters; ++it) {
+        const int ta = it % distinct;
+        const uint64_t da2 = make_kmajor_desc<32>(smem_u32(sA) + (uint32_t)(ta * M * 64));
+        const uint64_t db2 = make_kmajor_desc<32>(smem_u32(sB) + (uint32_t)(ta * N * 64));
+        for (int k = 0; k < 2; ++k) umma_bf16(tmem, da2 + 2 * k, db2 + 2 * k, idesc, (it | k) ? 1u : 0u);
+      }
+    } else
     for (int it = 0; it < iters; ++it)
       for (int k = 0; k < 2; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
     umma_commit(&bar);
@@ -68,10 +77,10 @@ static float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(
 
 template <int M, int N>
 void run(const std::vector<uint16_t>& hA, const std::vector<uint16_t>& hB, __nv_bfloat16* dA, __nv_bfloat16* dB, float* dD, long long* dC) {
-  const int smem = 128 * 64 + 256 * 64 + 1024;
+  const int smem = 4 * 128 * 64 + 4 * 256 * 64 + 1024;
   cudaFuncSetAttribute(probe_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaMemset(dD, 0, 128 * 256 * 4);
-  probe_kernel<M, N><<<1, 128, smem>>>(dA, dB, dD, 1, nullptr);
+  probe_kernel<M, N><<<1, 128, smem>>>(dA, dB, dD, 1, nullptr, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("M=%d N=%d: %s\n", M, N, cudaGetErrorString(e)); exit(1); }
   std::vector<float> hD(128 * N);
@@ -101,11 +110,11 @@ void run(const std::vector<uint16_t>& hA, const std::vector<uint16_t>& hB, __nv_
       printf(" %d", found);
     }
   }
-  for (int iters : {64, 512}) {
-    probe_kernel<M, N><<<1, 128, smem>>>(dA, dB, nullptr, iters, dC);
+  for (int distinct : {0, 4}) {
+    probe_kernel<M, N><<<1, 128, smem>>>(dA, dB, nullptr, 512, dC, distinct);
     cudaDeviceSynchronize();
     long long c; cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost);
-    printf("  | %d MMAs: %.1f clk/MMA", 2 * iters, (double)c / (2 * iters));
+    printf("  | %s operands: %.1f clk/MMA", distinct ? "4 distinct" : "same", (double)c / 1024);
   }
   printf("\n");
 }
