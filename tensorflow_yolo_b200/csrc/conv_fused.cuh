@@ -738,12 +738,17 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
 // on the pipe for a fifth of the producers' time), and it needs the operands in registers.
 //   warps 0-5   producer epilogue: TMEM lane quarter = warp & 3, M tile = warp >> 2 (pixels f = 128*mt + 32*q + lane < 180):
 //               D1 -> BN + leaky (zero outside the image: the 3x3 conv's padding) -> bf16 -> the three kw copies of A[tile&1]
-//   warps 8-11  consumer epilogue (fuse_epilogue_role): residual = centre of the patch, read from shared memory
-//   warp 12     one elected lane: L2 prefetch, patch loads, the 8 producer MMAs of tile i+1, then the 18 consumer MMAs of tile i
-// A patch stage is released by the four consumer-epilogue warps (the last readers).
+//   warp 6      one elected lane: L2 prefetch, patch loads, the 8 producer MMAs of tile i+1, then the 18 consumer MMAs of tile i
+//   warps 8-23  consumer epilogue, four warps per TMEM lane quarter with 16 channels each (the epilogue is latency-bound --
+//               dependent chains at one instruction per ~9 cycles -- so it is spread over many warps, scale / shift in
+//               registers): BN + leaky + residual (= centre of the patch, read from shared memory), one TMA store of
+//               [2 rows][16 cols][16 channels] per warp and tile
+// A patch stage is released by the sixteen consumer-epilogue warps (the last readers).
 constexpr int BLK_PROD_WARPS = 6;
-constexpr int BLK_EPI_WARP0 = 8, BLK_MMA_WARP = 12;
-constexpr int BLK_THREADS = (BLK_MMA_WARP + 1) * 32;                      // 416
+constexpr int BLK_MMA_WARP = 6;                                           // (warp 7 idles: the epilogue warps must start at a multiple of 4)
+constexpr int BLK_EPI_WARP0 = 8, BLK_EPI_WARPS = 16;
+constexpr int BLK_EPI_COLS = FUSE_COUT / (BLK_EPI_WARPS / 4);             // 16
+constexpr int BLK_THREADS = (BLK_EPI_WARP0 + BLK_EPI_WARPS) * 32;         // 768
 constexpr int BLK_W1_BYTES = FUSE_CMID * 128;                             // [32 couts][64 cin] bf16, SWIZZLE_128B: 4,096
 constexpr int BLK_TMEM_COLS = 256;                                        // [0,128): two consumer accumulators; [128,256): two x (2 M tiles x 32)
 constexpr int FUSE_SMEM_BLOCK = 1024 + FUSE_HEADER + FUSE_B_BYTES + BLK_W1_BYTES + 2 * BLOCK_A_BYTES + BLOCK_IN_STAGES * BLOCK_PATCH_STAGE + FUSE_EPI_BYTES;
@@ -785,14 +790,14 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.a_full[i], BLK_PROD_WARPS);
       mbar_init(&s.mma_done[i], 1);
-      mbar_init(&s.acc_empty[i], FUSE_EPI_WARPS);
+      mbar_init(&s.acc_empty[i], BLK_EPI_WARPS);
       mbar_init(&d1_full[i], 1);
       mbar_init(&d1_empty[i], BLK_PROD_WARPS);
     }
     mbar_init(s.b_full, 1);
     for (int i = 0; i < BLOCK_IN_STAGES; ++i) {
       mbar_init(&s.in_full[i], 1);
-      mbar_init(&s.in_empty[i], FUSE_EPI_WARPS);
+      mbar_init(&s.in_empty[i], BLK_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -885,8 +890,75 @@ block_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       atomicAdd(&a.dbg[FUSE_DBG_PROD_CONV], (unsigned long long)(t_conv - t_wait));
       atomicAdd(&a.dbg[FUSE_DBG_PROD_TOTAL], (unsigned long long)(clk() - t_begin));
     }
-  } else if (warp >= BLK_EPI_WARP0 && warp < BLK_MMA_WARP) {
-    fuse_epilogue_role<true, BLOCK_IN_STAGES, BLK_EPI_WARP0>(s, &tmOut, tmem_base, a, patch_u32, BLOCK_PATCH_STAGE);
+  } else if (warp >= BLK_EPI_WARP0) {
+    // ---- consumer epilogue: TMEM lane quarter = warp & 3 (tile rows 2q, 2q+1), channels [16 * part, 16 * part + 16) ----
+    const int quarter = warp & 3, ew = warp - BLK_EPI_WARP0, part = ew >> 2;
+    const bool dbg = a.dbg != nullptr && ew == 1 && lane == 0;
+    long long t_mma = 0;
+    const long long t_begin = dbg ? clk() : 0;
+    // residual position of this lane in the input patch: output pixel (2*quarter + lane/16, lane%16) -> patch pixel (+1, +1)
+    const int res_f = (2 * quarter + (lane >> 4) + 1) * BLOCK_PATCH_W + (lane & 15) + 1;
+    const uint32_t res_ofs = (uint32_t)res_f * 128u, res_sw = (uint32_t)res_f & 7u;
+    int res_stage = 0;
+    uint32_t res_phase = 0;
+    const bool leaky2 = a.leaky2 != 0;
+    uint64_t sc[BLK_EPI_COLS / 2], sh[BLK_EPI_COLS / 2];
+#pragma unroll
+    for (int j = 0; j < BLK_EPI_COLS / 2; ++j) {
+      sc[j] = f2_pack(a.scale2[part * BLK_EPI_COLS + 2 * j], a.scale2[part * BLK_EPI_COLS + 2 * j + 1]);
+      sh[j] = f2_pack(a.shift2[part * BLK_EPI_COLS + 2 * j], a.shift2[part * BLK_EPI_COLS + 2 * j + 1]);
+    }
+    TileWalk tw;
+    tw.init(a.tiles_w, a.tiles_h, blockIdx.x, gridDim.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      // staging: 32 pixels (this warp's two tile rows) x 32 bytes (16 channels), dense
+      uint8_t* buf = s.epi + (ew * 2 + (it & 1)) * 1024;
+      const uint32_t row = smem_u32(buf) + (uint32_t)lane * 32u;
+      if (lane == 0) tma_store_wait_read<1>();       // the store of two tiles ago has read this staging buffer
+      __syncwarp();
+      const long long t0 = dbg ? clk() : 0;
+      mbar_wait(&s.mma_done[acc], (uint32_t)(it >> 1) & 1u);
+      if (dbg) t_mma += clk() - t0;
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * FUSE_COUT + part * BLK_EPI_COLS), v);
+      const uint32_t res_row = patch_u32 + (uint32_t)(res_stage * BLOCK_PATCH_STAGE) + res_ofs;
+      mbar_wait(&s.in_full[res_stage], res_phase);   // long complete (the MMAs consumed the patch): orders the reads below
+      const uint4 r0 = lds128(res_row + (((uint32_t)(2 * part) ^ res_sw) << 4));
+      const uint4 r1 = lds128(res_row + (((uint32_t)(2 * part + 1) ^ res_sw) << 4));
+      tmem_ld_wait();
+      const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y0, y1;
+        bn_leaky2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), sc[j], sh[j], leaky2, y0, y1);
+        y0 += __uint_as_float(rw[j] << 16);
+        y1 += __uint_as_float(rw[j] & 0xFFFF0000u);
+        pk[j] = pack_bf16(y0, y1);
+      }
+      sts128(row, pk[0], pk[1], pk[2], pk[3]);
+      sts128(row + 16u, pk[4], pk[5], pk[6], pk[7]);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s.acc_empty[acc]);              // the accumulator is in registers / staging: hand it back early
+        mbar_arrive(&s.in_empty[res_stage]);
+        tma_store_4d(&tmOut, buf, part * BLK_EPI_COLS, tw.q0(), tw.p0() + 2 * quarter, tw.img);
+        tma_store_commit();
+      }
+      if (++res_stage == BLOCK_IN_STAGES) { res_stage = 0; res_phase ^= 1u; }
+      tw.advance();
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (dbg) {
+      atomicAdd(&a.dbg[FUSE_DBG_EPI_WAIT_MMA], (unsigned long long)t_mma);
+      atomicAdd(&a.dbg[FUSE_DBG_EPI_TOTAL], (unsigned long long)(clk() - t_begin));
+      atomicAdd(&a.dbg[FUSE_DBG_TILES], (unsigned long long)it);
+    }
   } else if (warp == BLK_MMA_WARP) {
     if (elect_one()) {
       const bool dbg_mma = a.dbg != nullptr;

@@ -1334,9 +1334,12 @@ static int build_tensor_maps(yb_engine* e) {
       }
       cuuint64_t dims[4] = {(cuuint64_t)op.cout, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)e->max_batch};
       cuuint64_t strides[3] = {(cuuint64_t)op.out.ld * 2, (cuuint64_t)op.Wo * op.out.ld * 2, (cuuint64_t)op.Ho * op.Wo * op.out.ld * 2};
-      cuuint32_t box[4] = {(cuuint32_t)FUSE_COUT, (cuuint32_t)FUSE_TW, 2, 1};      // 128-byte rows: SWIZZLE_128B
+      // stem: one box of [2 rows][16 cols][64 channels] per epilogue warp (128-byte rows, SWIZZLE_128B); block: sixteen
+      // epilogue warps, [2 rows][16 cols][16 channels] each, dense 32-byte rows
+      const bool blk = op.fuse_kind == FUSE_BLOCK;
+      cuuint32_t box[4] = {(cuuint32_t)(blk ? BLK_EPI_COLS : FUSE_COUT), (cuuint32_t)FUSE_TW, 2, 1};
       r = g_encode_tiled(&op.tmOut4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, view_ptr(e, op.out), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, blk ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(YB_ERR_CUDA, "cuTensorMapEncodeTiled(4-D output) failed (%d) for layer %d", (int)r, op.layer);
       memset(&op.tmIn4, 0, sizeof(op.tmIn4));
