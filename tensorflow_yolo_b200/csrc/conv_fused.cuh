@@ -191,38 +191,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void producer_bar() {          // named barrier 1: the producer threads only
   asm volatile("bar.sync 1, %0;" ::"n"(FUSE_PRODUCER_THREADS) : "memory");
 }
-// packed fp32 pairs (sm_100): one instruction, two IEEE operations
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// y = acc * scale + shift; leaky: max(y, 0.1 y) -- the scalar epilogue's operations (FFMA, FMUL, FMNMX), two lanes at a time
-__device__ __forceinline__ void bn_leaky2(float a0, float a1, uint64_t sc, uint64_t sh, bool leaky, float& y0, float& y1) {
-  const uint64_t y = f2_fma(f2_pack(a0, a1), sc, sh);
-  f2_unpack(y, y0, y1);
-  if (leaky) {
-    float z0, z1;
-    f2_unpack(f2_mul(y, f2_pack(0.1f, 0.1f)), z0, z1);
-    y0 = fmaxf(y0, z0); y1 = fmaxf(y1, z1);
-  }
-}
 // byte offset of 16-byte chunk t of operand row `row` (64-byte rows, SWIZZLE_64B: chunk ^= (row >> 1) & 3) -- the
 // layout TMA writes and make_kmajor_desc<32> describes; the operand buffers are 1024-byte aligned
 __device__ __forceinline__ uint32_t operand_ofs(int row, int t) { return (uint32_t)(row * 64 + ((t ^ ((row >> 1) & 3)) << 4)); }

@@ -259,6 +259,39 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// packed fp32 pairs (sm_100): one instruction, two IEEE operations
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// y = acc * scale + shift; leaky: max(y, 0.1 y) -- the scalar epilogue's operations (FFMA, FMUL, FMNMX), two lanes at a time
+__device__ __forceinline__ void bn_leaky2(float a0, float a1, uint64_t sc, uint64_t sh, bool leaky, float& y0, float& y1) {
+  const uint64_t y = f2_fma(f2_pack(a0, a1), sc, sh);
+  f2_unpack(y, y0, y1);
+  if (leaky) {
+    float z0, z1;
+    f2_unpack(f2_mul(y, f2_pack(0.1f, 0.1f)), z0, z1);
+    y0 = fmaxf(y0, z0); y1 = fmaxf(y1, z1);
+  }
+}
+
 // ================================================================================================
 // Persistent kernel: one CTA per SM loops over output tiles.  Two TMEM accumulator buffers let the
 // epilogue of tile i (TMEM -> registers -> global) overlap the mainloop of tile i+1, the TMA producer
@@ -678,11 +711,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (dbg) { const long long t1 = clk(); t_ld += t1 - t0; t0 = t1; }
           const int cbase = n0 + chunk * 32;
           float f[32];
+          {   // BN + leaky on packed fp32 pairs (FFMA2 / FMUL2: the scalar operations, two per instruction)
+            const bool leaky = a.leaky != 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = __uint_as_float(v[j]) * s_scale[cbase + j] + s_shift[cbase + j];
-            if (a.leaky) y = fmaxf(y, 0.1f * y);
-            f[j] = y;
+            for (int j = 0; j < 32; j += 2) {
+              const float2 sc = *reinterpret_cast<const float2*>(&s_scale[cbase + j]);
+              const float2 sh = *reinterpret_cast<const float2*>(&s_shift[cbase + j]);
+              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y), leaky, f[j], f[j + 1]);
+            }
           }
           if (has_res_t) {
 #pragma unroll
@@ -782,11 +818,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int cbase = n0 + chunk * 32;
         if (valid && cbase < a.cout) {
           float f[32];
+          {
+            const bool leaky = a.leaky != 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float y = __uint_as_float(v[j]) * s_scale[cbase + j] + s_shift[cbase + j];
-            if (a.leaky) y = fmaxf(y, 0.1f * y);
-            f[j] = y;
+            for (int j = 0; j < 32; j += 2) {
+              const float2 sc = *reinterpret_cast<const float2*>(&s_scale[cbase + j]);
+              const float2 sh = *reinterpret_cast<const float2*>(&s_shift[cbase + j]);
+              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y), leaky, f[j], f[j + 1]);
+            }
           }
           if (has_res) {
 #pragma unroll
