@@ -368,8 +368,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* b_full_bar = tmem_empty_bar + 2;                    // [1]
   uint64_t* res_bar = b_full_bar + 1;                           // [EPI_WARPS][2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * CONV_TCP_EPI_WARPS);
-  float* s_scale = reinterpret_cast<float*>(smem + 1024);
-  float* s_shift = s_scale + CONV_TCP_MAX_COUT_PAD;
+  // BN scale / shift per channel pair, interleaved {scale[c], scale[c+1], shift[c], shift[c+1]}: one 16-byte broadcast load
+  // per pair in the epilogue
+  float4* s_ss = reinterpret_cast<float4*>(smem + 1024);
   const int num_k = a.taps * a.kc_blocks;
   const int n_stages = pa.n_stages;
   const bool bstat = pa.b_stationary != 0;
@@ -409,8 +410,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     else tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   }
   for (int i = threadIdx.x; i < pa.cout_pad; i += CONV_TCP_THREADS) {
-    s_scale[i] = a.scale[i];
-    s_shift[i] = a.shift[i];
+    reinterpret_cast<float*>(s_ss)[(i >> 1) * 4 + (i & 1)] = a.scale[i];
+    reinterpret_cast<float*>(s_ss)[(i >> 1) * 4 + 2 + (i & 1)] = a.shift[i];
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();
@@ -715,9 +716,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const bool leaky = a.leaky != 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float2 sc = *reinterpret_cast<const float2*>(&s_scale[cbase + j]);
-              const float2 sh = *reinterpret_cast<const float2*>(&s_shift[cbase + j]);
-              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y), leaky, f[j], f[j + 1]);
+              const float4 ss = s_ss[(cbase + j) >> 1];
+              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(ss.x, ss.y), f2_pack(ss.z, ss.w), leaky, f[j], f[j + 1]);
             }
           }
           if (has_res_t) {
@@ -725,10 +725,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int g = 0; g < 4; ++g) {
               const uint32_t rw[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
-                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
-              }
+              for (int j = 0; j < 4; ++j)      // two bf16 -> fp32 and one packed add per channel pair
+                f2_unpack(f2_add(f2_pack(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]),
+                                 f2_pack(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u))),
+                          f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
             }
           }
           if (a.out_f32) {
@@ -822,9 +822,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const bool leaky = a.leaky != 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float2 sc = *reinterpret_cast<const float2*>(&s_scale[cbase + j]);
-              const float2 sh = *reinterpret_cast<const float2*>(&s_shift[cbase + j]);
-              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y), leaky, f[j], f[j + 1]);
+              const float4 ss = s_ss[(cbase + j) >> 1];
+              bn_leaky2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f2_pack(ss.x, ss.y), f2_pack(ss.z, ss.w), leaky, f[j], f[j + 1]);
             }
           }
           if (has_res) {
@@ -832,10 +831,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int g = 0; g < 4; ++g) {
               const uint32_t rw[4] = {rcur[g].x, rcur[g].y, rcur[g].z, rcur[g].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[g * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
-                f[g * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
-              }
+              for (int j = 0; j < 4; ++j)      // two bf16 -> fp32 and one packed add per channel pair
+                f2_unpack(f2_add(f2_pack(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]),
+                                 f2_pack(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u))),
+                          f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
             }
           }
           if (a.out_f32) {
